@@ -1,0 +1,275 @@
+"""Python host side of the drop-in boundary: `GLWrapper`, method for method.
+
+Mirrors the public interface of the reference's render driver
+(src/GLWrapper.h:17-38) on top of the C-ABI in include/rtb200.h — the same
+library the C++ host (host/GLWrapper.cpp) calls.  The reference's error
+behaviour is "print and exit" (utils.h:25,62; GLWrapper.cpp:371-375); here every
+failing call raises `RtbError` carrying rtb_last_error().
+
+There is no CPU path: if librtb200.so is missing, or no sm_100 device is
+present, construction / init_window() raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .scene import UBO_BLOCKS, rt_defines
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librtb200.so")
+
+KERNEL_AUTO, KERNEL_QUAD, KERNEL_PERSISTENT = 0, 1, 2
+
+
+class RtbError(RuntimeError):
+    pass
+
+
+class RtbStats(C.Structure):
+    _fields_ = [("pixels", C.c_uint64), ("rays_nearest", C.c_uint64), ("rays_shadow", C.c_uint64), ("tests", C.c_uint64 * 7),
+                ("dk_iterations", C.c_uint64), ("shaded_hits", C.c_uint64 * 7), ("light_evals", C.c_uint64),
+                ("flops", C.c_double), ("kernel_ms", C.c_float), ("kernel_used", C.c_int32), ("grid", C.c_int32),
+                ("block", C.c_int32), ("smem_bytes", C.c_int32)]
+
+    def as_dict(self):
+        return {"pixels": self.pixels, "rays_nearest": self.rays_nearest, "rays_shadow": self.rays_shadow,
+                "tests": list(self.tests), "dk_iterations": self.dk_iterations, "shaded_hits": list(self.shaded_hits),
+                "light_evals": self.light_evals, "flops": self.flops, "kernel_ms": self.kernel_ms,
+                "kernel_used": self.kernel_used, "grid": self.grid, "block": self.block, "smem_bytes": self.smem_bytes}
+
+    @property
+    def rays(self):
+        return self.rays_nearest + self.rays_shadow
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load librtb200.so (built in-tree by __graft_entry__.build() / make -C csrc).  Fails loudly when absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RtbError(f"{LIB_PATH} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback for the ray-trace pass)")
+    L = C.CDLL(LIB_PATH)
+    vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
+    L.rtb_create.restype = vp
+    L.rtb_create.argtypes = [i, i, i]
+    L.rtb_destroy.argtypes = [vp]
+    L.rtb_set_partition.argtypes = [vp, i, i, i]
+    L.rtb_local_rows.argtypes = [vp]
+    L.rtb_set_defines.argtypes = [vp, vp]
+    L.rtb_upload.argtypes = [vp, i, vp, sz]
+    L.rtb_set_cubemap.argtypes = [vp, C.POINTER(vp), i, i, i]
+    L.rtb_set_texture2d.argtypes = [vp, i, vp, i, i, i]
+    L.rtb_set_option.argtypes = [vp, C.c_char_p, i]
+    L.rtb_render.argtypes = [vp]
+    L.rtb_render_to.argtypes = [vp, vp, vp]
+    L.rtb_render_counted.argtypes = [vp, C.POINTER(RtbStats)]
+    L.rtb_sync.argtypes = [vp]
+    L.rtb_read_rgba32f.argtypes = [vp, vp]
+    L.rtb_read_rgba8.argtypes = [vp, vp]
+    L.rtb_device_framebuffer.restype = vp
+    L.rtb_device_framebuffer.argtypes = [vp]
+    L.rtb_get_stats.argtypes = [vp, C.POINTER(RtbStats)]
+    L.rtb_measure_fp32_peak.argtypes = [i, C.POINTER(C.c_double)]
+    L.rtb_last_error.restype = C.c_char_p
+    L.rtb_last_error.argtypes = [vp]
+    L.rtb_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def measure_fp32_peak(device: int = 0) -> float:
+    """FFMA-only microbenchmark, TFLOP/s."""
+    L = load_library()
+    out = C.c_double(0)
+    if L.rtb_measure_fp32_peak(device, C.byref(out)) != 0:
+        raise RtbError("rtb_measure_fp32_peak failed (no CUDA device?)")
+    return out.value
+
+
+class GLWrapper:
+    """src/GLWrapper.h, same method names; `draw()` launches the CUDA ray-trace pass."""
+
+    def __init__(self, width: int, height: int, fullScreen: bool = False, device: int = 0):
+        self._L = load_library()
+        self.width, self.height = int(width), int(height)
+        self.device = device
+        self._ctx = None
+        self._ubos = {}                 # handle -> binding (update_buffer is static and only gets the handle)
+        self._next_handle = 1
+        self._textures = {}             # handle -> unit
+        self._skybox = None
+        self.window = self              # GLFWwindow* stand-in
+
+    # -- GLWrapper.h:21-23
+    def getWidth(self):
+        return self.width
+
+    def getHeight(self):
+        return self.height
+
+    def getProgramId(self):
+        return 1
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RtbError(self._L.rtb_last_error(self._ctx).decode() or f"rtb error {rc}")
+
+    # -- GLWrapper.h:25  (GLWrapper.cpp:61-133: create context)
+    def init_window(self) -> bool:
+        self._ctx = self._L.rtb_create(self.width, self.height, self.device)
+        if not self._ctx:
+            raise RtbError(self._L.rtb_last_error(None).decode())
+        return True
+
+    # -- GLWrapper.h:30: SMAA is out of scope (BASELINE.json north_star); accepted and ignored
+    def enable_SMAA(self, preset=None):
+        pass
+
+    # -- GLWrapper.h:26  (GLWrapper.cpp:232-247)
+    def init_shaders(self, defines):
+        d = np.ascontiguousarray(np.asarray(defines, dtype=rt_defines)).reshape(1)
+        self._check(self._L.rtb_set_defines(self._ctx, d.ctypes.data))
+
+    # -- GLWrapper.h:35,27  (GLWrapper.cpp:284-317, 135-141).  `faces`: 6 decoded uint8 arrays [h,w,ch]
+    def load_cubemap(self, faces, genMipmap: bool = False):
+        faces = [np.ascontiguousarray(f, dtype=np.uint8) for f in faces]
+        if len(faces) != 6:
+            raise RtbError("a cubemap has six faces")
+        h, w, ch = faces[0].shape
+        arr = (C.c_void_p * 6)(*[f.ctypes.data for f in faces])
+        self._check(self._L.rtb_set_cubemap(self._ctx, arr, w, h, ch))
+        self._skybox = self._next_handle
+        self._next_handle += 1
+        return self._skybox
+
+    def set_skybox(self, textureId):
+        self._skybox = textureId
+
+    # -- GLWrapper.h:36  (GLWrapper.cpp:356-363).  `pixels`: decoded uint8 [h,w,ch]; texNum = texture unit 1..5
+    def load_texture(self, texNum: int, pixels, uniformName: str = "", wrapMode=None):
+        a = np.ascontiguousarray(pixels, dtype=np.uint8)
+        h, w, ch = a.shape
+        self._check(self._L.rtb_set_texture2d(self._ctx, texNum, a.ctypes.data, w, h, ch))
+        handle = self._next_handle
+        self._next_handle += 1
+        self._textures[handle] = texNum
+        return handle
+
+    # -- GLWrapper.h:37  (GLWrapper.cpp:365-379).  Returns the ubo handle (the reference writes it through GLuint*).
+    def init_buffer(self, name: str, bindingPoint: int, data) -> int:
+        if name not in UBO_BLOCKS:
+            raise RtbError(f"Invalid ubo block name '{name}'")           # GLWrapper.cpp:371-375
+        if UBO_BLOCKS[name][0] != bindingPoint:
+            raise RtbError(f"block {name} is bound at {UBO_BLOCKS[name][0]}, not {bindingPoint}")
+        handle = self._next_handle
+        self._next_handle += 1
+        self._ubos[handle] = bindingPoint
+        if data is None:
+            self._check(self._L.rtb_upload(self._ctx, bindingPoint, None, UBO_BLOCKS[name][1].itemsize if bindingPoint == 0 else 0))
+        else:
+            self.update_buffer(handle, data)
+        return handle
+
+    # -- GLWrapper.h:38  (GLWrapper.cpp:381-386)
+    def update_buffer(self, ubo: int, data):
+        a = np.ascontiguousarray(data)
+        self._check(self._L.rtb_upload(self._ctx, self._ubos[ubo], a.ctypes.data if a.nbytes else None, a.nbytes))
+
+    # -- GLWrapper.h:34  (GLWrapper.cpp:155-165)
+    def draw(self):
+        self._check(self._L.rtb_render(self._ctx))
+
+    # -- GLWrapper.h:29
+    def stop(self):
+        if self._ctx:
+            self._L.rtb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.stop()
+        except Exception:
+            pass
+
+    # ---- beyond the reference: read-back, options, multi-GPU partition, statistics ----
+    def set_option(self, key: str, value: int):
+        self._check(self._L.rtb_set_option(self._ctx, key.encode(), int(value)))
+
+    def set_partition(self, rank: int, world: int, block_rows: int = 16):
+        self._check(self._L.rtb_set_partition(self._ctx, rank, world, block_rows))
+
+    def local_rows(self) -> int:
+        return self._L.rtb_local_rows(self._ctx)
+
+    def sync(self):
+        self._check(self._L.rtb_sync(self._ctx))
+
+    def read_pixels(self) -> np.ndarray:
+        """RGBA32F [local_rows, W, 4]; row 0 = bottom scanline of this rank's first block."""
+        out = np.empty((self.local_rows(), self.width, 4), dtype=np.float32)
+        self._check(self._L.rtb_read_rgba32f(self._ctx, out.ctypes.data))
+        return out
+
+    def read_pixels_u8(self) -> np.ndarray:
+        out = np.empty((self.local_rows(), self.width, 4), dtype=np.uint8)
+        self._check(self._L.rtb_read_rgba8(self._ctx, out.ctypes.data))
+        return out
+
+    def draw_to(self, device_ptr: int, stream: int = 0):
+        """Render into a caller-owned device buffer (e.g. a torch tensor's data_ptr) on a caller stream."""
+        self._check(self._L.rtb_render_to(self._ctx, device_ptr, stream or None))
+
+    def draw_counted(self) -> RtbStats:
+        st = RtbStats()
+        self._check(self._L.rtb_render_counted(self._ctx, C.byref(st)))
+        return st
+
+    def stats(self) -> RtbStats:
+        st = RtbStats()
+        self._check(self._L.rtb_get_stats(self._ctx, C.byref(st)))
+        return st
+
+    def device_framebuffer(self) -> int:
+        return self._L.rtb_device_framebuffer(self._ctx)
+
+
+def setup_scene(gl: GLWrapper, scene, textures=None):
+    """What main.cpp + SceneManager::init do with a scene_container: init_shaders, samplers, init_buffers
+    (main.cpp:134-156, SceneManager.cpp:244-255) followed by one update_buffers (SceneManager.cpp:266-276)."""
+    gl.init_shaders(scene.get_defines())
+    if textures is not None:
+        if textures.cube is not None:
+            gl.set_skybox(gl.load_cubemap(textures.cube, False))
+        for unit, px in sorted(textures.tex2d.items()):
+            gl.load_texture(unit, px, "")
+    handles = {}
+    handles["scene_buf"] = gl.init_buffer("scene_buf", 0, None)
+    for name, attr in (("spheres_buf", "spheres"), ("planes_buf", "planes"), ("surfaces_buf", "surfaces"), ("boxes_buf", "boxes"),
+                       ("toruses_buf", "toruses"), ("rings_buf", "rings"), ("lights_point_buf", "lights_point"),
+                       ("lights_direct_buf", "lights_direct")):
+        handles[name] = gl.init_buffer(name, UBO_BLOCKS[name][0], scene.array(attr))
+    gl.update_buffer(handles["scene_buf"], np.ascontiguousarray(scene.scene).reshape(1))
+    return handles
+
+
+def gather_rows(parts, height: int, world: int, block_rows: int = 16) -> np.ndarray:
+    """Re-interleave per-rank packed scanlines (list indexed by rank, each [local_rows, W, 4]) into the full frame."""
+    w = parts[0].shape[1]
+    out = np.empty((height, w, 4), dtype=parts[0].dtype)
+    cursor = [0] * world
+    b = 0
+    while b * block_rows < height:
+        r = b % world
+        n = min(block_rows, height - b * block_rows)
+        out[b * block_rows:b * block_rows + n] = parts[r][cursor[r]:cursor[r] + n]
+        cursor[r] += n
+        b += 1
+    return out

@@ -1,0 +1,27 @@
+/* rt_launch.h — launch geometry shared by the kernels and the host API. */
+#ifndef RT_LAUNCH_H
+#define RT_LAUNCH_H
+
+#include <cuda_runtime.h>
+#include "rt_params.h"
+
+#define QUAD_THREADS 128
+#define PERSIST_THREADS 128
+#define RTB_LAUNCH_QUAD 1
+#define RTB_LAUNCH_PERSISTENT 2
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* strict build (-fmad=false) */
+int rtb_strict_launch_pack(const FrameParams* P, uint8_t* dst, cudaStream_t st);
+int rtb_strict_launch(const FrameParams* P, int kernel, int counted, int grid, int threads, size_t smem, cudaStream_t st);
+int rtb_strict_occupancy(int kernel, size_t smem, int* blocks_per_sm);
+/* fast build */
+int rtb_fast_launch_pack(const FrameParams* P, uint8_t* dst, cudaStream_t st);
+int rtb_fast_launch(const FrameParams* P, int kernel, int counted, int grid, int threads, size_t smem, cudaStream_t st);
+int rtb_fast_occupancy(int kernel, size_t smem, int* blocks_per_sm);
+#ifdef __cplusplus
+}
+#endif
+#endif

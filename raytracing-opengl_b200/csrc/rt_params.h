@@ -1,0 +1,73 @@
+/* rt_params.h — host/device shared description of one frame's inputs.
+ *
+ * The std140 arrays uploaded through rtb_upload() (include/rtb200_types.h) stay
+ * in HBM untouched ("raw"); a tiny pack kernel derives from them the HOT
+ * geometry records below — everything the linear scan of rt.frag:587-658
+ * touches, nothing it does not (the 64-byte material of every primitive is
+ * cold: it is read once per shaded hit, from the raw arrays).  The packed
+ * block is what each persistent CTA stages into shared memory with one TMA
+ * bulk copy.  Every record is a multiple of 16 bytes.
+ *
+ * Squares that the shader recomputes per test (r*r, R*R) are stored squared:
+ * the same single fp32 multiply, done once — results are bit-identical.
+ */
+#ifndef RT_PARAMS_H
+#define RT_PARAMS_H
+
+#include <stdint.h>
+#include "../../include/rtb200_types.h"
+
+struct PSphere { float cx, cy, cz, r2; };                                   /* 16 B; hollow flags in a side bitmask */
+struct PPlane  { float nx, ny, nz, _0, px, py, pz, _1; };                    /* 32 B */
+struct PBox    { float qx, qy, qz, qw, px, py, pz, fx, fy, fz; int32_t tex; int32_t _0; };      /* 48 B */
+struct PTorus  { float qx, qy, qz, qw, px, py, pz, R2, r2, _0, _1, _2; };    /* 48 B */
+struct PRing   { float qx, qy, qz, qw, px, py, pz, r1, r2; int32_t tex; int32_t _0, _1; };      /* 48 B */
+struct PSurf   { float qx, qy, qz, qw, px, py, pz, a, b, c, d, e, f, minx, miny, minz, maxx, maxy, maxz, _0; }; /* 80 B */
+struct PLight  { float x, y, z, r2; };                                       /* 16 B */
+
+/* byte offsets of each section inside the packed block (all multiples of 16) */
+struct PackedLayout {
+    uint32_t off_plane, off_sphere, off_hollow, off_surf, off_box, off_torus, off_ring, off_light;
+    uint32_t total_bytes;
+};
+
+struct TexDesc {                      /* one mip-mapped RGBA8 2-D texture in HBM */
+    const uint8_t* base;              /* NULL = unit not bound */
+    int32_t w, h, levels;
+    uint32_t level_off[16];           /* byte offset of each level */
+};
+
+struct CubeDesc {
+    const uint8_t* base;              /* 6 RGBA8 faces, face f at base + f*w*h*4; NULL = unbound */
+    int32_t w, h;
+};
+
+struct FrameParams {
+    /* specialisation constants (rt.frag:122-132) */
+    int32_t n_sphere, n_plane, n_surf, n_box, n_torus, n_ring, n_lpoint, n_ldirect, iterations;
+    float ambient[3], shadow_ambient[3];
+    /* scene uniform (rt.frag:104-113) */
+    float cam_q[4], cam_pos[3];
+    int32_t canvas_w, canvas_h;
+    /* raw std140 arrays in HBM */
+    const rtb_sphere* spheres; const rtb_plane* planes; const rtb_surface* surfaces; const rtb_box* boxes;
+    const rtb_torus* toruses; const rtb_ring* rings; const rtb_light_point* lights_point; const rtb_light_direct* lights_direct;
+    /* packed hot geometry */
+    const uint8_t* packed; PackedLayout lay;
+    /* samplers */
+    CubeDesc cube; TexDesc tex[6];
+    /* output: this rank's scanlines, packed in block order (rtb_set_partition) */
+    float* fb; int32_t rank, world, block_rows, local_rows;
+    /* work distribution */
+    unsigned int* tile_counter; int32_t n_tiles_x, n_tiles_y;
+    /* options */
+    int32_t cull;
+    unsigned long long* counters;     /* NULL unless the counting variant runs; layout = enum CounterSlot */
+};
+
+enum CounterSlot {
+    CNT_RAYS_NEAREST = 0, CNT_RAYS_SHADOW = 1, CNT_TESTS0 = 2 /* ..8 */, CNT_DK = 9, CNT_SHADED0 = 10 /* ..16 */,
+    CNT_LIGHT_EVALS = 17, CNT_PIXELS = 18, CNT_NUM = 19
+};
+
+#endif

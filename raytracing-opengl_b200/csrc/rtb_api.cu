@@ -1,0 +1,473 @@
+/* rtb_api.cu — the C-ABI of include/rtb200.h: context, uploads, sampler setup, launches.
+ *
+ * Each entry point replaces one GLWrapper method of the reference (cited in
+ * include/rtb200.h).  There is no CPU rendering path in this library: every
+ * frame is produced by the sm_100a kernels in rt_kernels.cu.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rtb200.h"
+#include "rt_launch.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct Tex2D { uint8_t* dev = nullptr; int w = 0, h = 0, levels = 0; uint32_t off[16] = { 0 }; };
+
+}  // namespace
+
+struct rtb_ctx {
+    int device = 0, n_sm = 0;
+    int width = 0, height = 0;
+    int rank = 0, world = 1, block_rows = 16, local_rows = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_upload = nullptr;
+    bool have_defines = false;
+    rtb_defines defines = {};
+    void* raw[RTB_NUM_BINDINGS] = { nullptr };
+    size_t raw_cap[RTB_NUM_BINDINGS] = { 0 }, raw_bytes[RTB_NUM_BINDINGS] = { 0 };
+    std::vector<uint8_t> shadow[RTB_NUM_BINDINGS];      /* host copies (scene uniform, textureNum inspection) */
+    uint8_t* packed = nullptr; size_t packed_cap = 0;
+    bool dirty = true;
+    unsigned int* tile_counter = nullptr;
+    unsigned long long* counters = nullptr;
+    float* fb = nullptr; size_t fb_floats = 0;
+    uint8_t* cube = nullptr; int cube_w = 0, cube_h = 0;
+    Tex2D tex[6];
+    int opt_kernel = RTB_KERNEL_AUTO, opt_strict = 0, opt_cull = 0, opt_ctas_per_sm = 0;
+    rtb_stats stats = {};
+    bool timed_pending = false;
+    std::string err;
+};
+
+namespace {
+
+int fail(rtb_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(ctx, RTB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+const size_t ELEM_SIZE[RTB_NUM_BINDINGS] = { sizeof(rtb_scene), sizeof(rtb_sphere), sizeof(rtb_plane), sizeof(rtb_surface), sizeof(rtb_box),
+                                             sizeof(rtb_torus), sizeof(rtb_ring), sizeof(rtb_light_point), sizeof(rtb_light_direct) };
+
+uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
+
+int compute_local_rows(int height, int rank, int world, int block_rows) {
+    int rows = 0;
+    for (int b = rank; b * block_rows < height; b += world) {
+        int r = height - b * block_rows;
+        rows += r < block_rows ? r : block_rows;
+    }
+    return rows;
+}
+
+/* GLWrapper::to_string (GLWrapper.cpp:279-282): the colour reaches the shader as the text "%f" */
+float round_through_percent_f(float v) {
+    char buf[64];
+    snprintf(buf, sizeof buf, "%f", v);
+    return strtof(buf, nullptr);
+}
+
+/* glGenerateMipmap stand-in: 2x2 box filter, floor(d/2) sizes, 8-bit round-half-up (DESIGN.md "samplers") */
+void build_mip_chain(const uint8_t* src, int w, int h, int ch, std::vector<uint8_t>& out, Tex2D& t) {
+    std::vector<uint8_t> cur((size_t)w * h * 4);
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        uint8_t r = src[i * ch], g = 0, b = 0, a = 255;
+        if (ch >= 3) { g = src[i * ch + 1]; b = src[i * ch + 2]; }
+        if (ch == 2) g = src[i * ch + 1];
+        if (ch == 4) a = src[i * ch + 3];
+        cur[i * 4] = r; cur[i * 4 + 1] = g; cur[i * 4 + 2] = b; cur[i * 4 + 3] = a;
+    }
+    out.clear();
+    t.w = w; t.h = h; t.levels = 0;
+    int cw = w, chh = h;
+    for (;;) {
+        t.off[t.levels++] = (uint32_t)out.size();
+        out.insert(out.end(), cur.begin(), cur.end());
+        if ((cw == 1 && chh == 1) || t.levels >= 16) break;
+        int nw = cw > 1 ? cw / 2 : 1, nh = chh > 1 ? chh / 2 : 1;
+        std::vector<uint8_t> nxt((size_t)nw * nh * 4);
+        for (int y = 0; y < nh; y++)
+            for (int x = 0; x < nw; x++) {
+                int x0 = cw > 1 ? 2 * x : 0, x1 = cw > 1 ? 2 * x + 1 : 0;
+                int y0 = chh > 1 ? 2 * y : 0, y1 = chh > 1 ? 2 * y + 1 : 0;
+                for (int c = 0; c < 4; c++) {
+                    int s = cur[((size_t)y0 * cw + x0) * 4 + c] + cur[((size_t)y0 * cw + x1) * 4 + c] +
+                            cur[((size_t)y1 * cw + x0) * 4 + c] + cur[((size_t)y1 * cw + x1) * 4 + c];
+                    nxt[((size_t)y * nw + x) * 4 + c] = (uint8_t)((s + 2) >> 2);
+                }
+            }
+        cur.swap(nxt);
+        cw = nw; chh = nh;
+    }
+}
+
+bool scene_uses_textures(const rtb_ctx* c) {
+    const rtb_defines& d = c->defines;
+    auto n_ok = [&](int binding, int n) { return c->shadow[binding].size() >= (size_t)n * ELEM_SIZE[binding]; };
+    if (n_ok(RTB_BIND_SPHERES, d.sphere_size))
+        for (int i = 0; i < d.sphere_size; i++) if (((const rtb_sphere*)c->shadow[RTB_BIND_SPHERES].data())[i].textureNum != 0) return true;
+    if (n_ok(RTB_BIND_BOXES, d.box_size))
+        for (int i = 0; i < d.box_size; i++) if (((const rtb_box*)c->shadow[RTB_BIND_BOXES].data())[i].textureNum != 0) return true;
+    if (n_ok(RTB_BIND_RINGS, d.ring_size))
+        for (int i = 0; i < d.ring_size; i++) if (((const rtb_ring*)c->shadow[RTB_BIND_RINGS].data())[i].textureNum != 0) return true;
+    return false;
+}
+
+PackedLayout make_layout(const rtb_defines& d) {
+    PackedLayout L;
+    uint32_t o = 0;
+    L.off_plane = o;  o += align16(d.plane_size * sizeof(PPlane));
+    L.off_sphere = o; o += align16(d.sphere_size * sizeof(PSphere));
+    L.off_hollow = o; o += align16(((d.sphere_size + 31) / 32) * 4);
+    L.off_surf = o;   o += align16(d.surface_size * sizeof(PSurf));
+    L.off_box = o;    o += align16(d.box_size * sizeof(PBox));
+    L.off_torus = o;  o += align16(d.torus_size * sizeof(PTorus));
+    L.off_ring = o;   o += align16(d.ring_size * sizeof(PRing));
+    L.off_light = o;  o += align16(d.light_point_size * sizeof(PLight));
+    L.total_bytes = o < 16 ? 16 : o;
+    return L;
+}
+
+/* algorithmic flop constants of the brute-force algorithm */
+double algorithmic_flops(const rtb_stats& s) {
+    double f = 0.0;
+    f += 19.0 * (double)s.tests[RTB_TYPE_SPHERE] + 16.0 * (double)s.tests[RTB_TYPE_PLANE] + 168.0 * (double)s.tests[RTB_TYPE_SURFACE] +
+         134.0 * (double)s.tests[RTB_TYPE_BOX] + 123.0 * (double)s.tests[RTB_TYPE_RING] + 19.0 * (double)s.tests[RTB_TYPE_POINT_LIGHT];
+    f += 130.0 * (double)s.tests[RTB_TYPE_TORUS] + 271.0 * (double)s.dk_iterations;
+    f += 60.0 * (double)s.light_evals;
+    f += 15.0 * (double)s.shaded_hits[RTB_TYPE_SPHERE] + 74.0 * (double)s.shaded_hits[RTB_TYPE_BOX] + 206.0 * (double)s.shaded_hits[RTB_TYPE_SURFACE] +
+         200.0 * (double)s.shaded_hits[RTB_TYPE_TORUS] + 68.0 * (double)s.shaded_hits[RTB_TYPE_RING];
+    f += 71.0 * (double)s.pixels;
+    return f;
+}
+
+int do_render(rtb_ctx* ctx, float* target, cudaStream_t st, bool counted, bool timed) {
+    if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "null context");
+    if (!ctx->have_defines) return fail(ctx, RTB_ERR_STATE, "rtb_render before rtb_set_defines (init_shaders)");
+    const rtb_defines& d = ctx->defines;
+    if (ctx->shadow[RTB_BIND_SCENE].size() < sizeof(rtb_scene)) return fail(ctx, RTB_ERR_STATE, "scene_buf was never uploaded");
+    const int counts[RTB_NUM_BINDINGS] = { 1, d.sphere_size, d.plane_size, d.surface_size, d.box_size, d.torus_size, d.ring_size,
+                                           d.light_point_size, d.light_direct_size };
+    for (int b = 0; b < RTB_NUM_BINDINGS; b++)
+        if (ctx->raw_bytes[b] < (size_t)counts[b] * ELEM_SIZE[b])
+            return fail(ctx, RTB_ERR_STATE, "binding %d holds %zu bytes, the defines need %zu", b, ctx->raw_bytes[b], (size_t)counts[b] * ELEM_SIZE[b]);
+    CU(cudaSetDevice(ctx->device));
+
+    FrameParams P;
+    memset(&P, 0, sizeof P);
+    P.n_sphere = d.sphere_size; P.n_plane = d.plane_size; P.n_surf = d.surface_size; P.n_box = d.box_size; P.n_torus = d.torus_size;
+    P.n_ring = d.ring_size; P.n_lpoint = d.light_point_size; P.n_ldirect = d.light_direct_size; P.iterations = d.iterations;
+    for (int i = 0; i < 3; i++) { P.ambient[i] = round_through_percent_f(d.ambient_color[i]); P.shadow_ambient[i] = round_through_percent_f(d.shadow_ambient[i]); }
+    const rtb_scene* sc = (const rtb_scene*)ctx->shadow[RTB_BIND_SCENE].data();
+    memcpy(P.cam_q, sc->quat_camera_rotation, 16);
+    memcpy(P.cam_pos, sc->camera_pos, 12);
+    P.canvas_w = sc->canvas_width; P.canvas_h = sc->canvas_height;
+    if (P.canvas_w != ctx->width || P.canvas_h != ctx->height)
+        return fail(ctx, RTB_ERR_STATE, "scene canvas %dx%d differs from the context's %dx%d", P.canvas_w, P.canvas_h, ctx->width, ctx->height);
+    P.spheres = (const rtb_sphere*)ctx->raw[RTB_BIND_SPHERES]; P.planes = (const rtb_plane*)ctx->raw[RTB_BIND_PLANES];
+    P.surfaces = (const rtb_surface*)ctx->raw[RTB_BIND_SURFACES]; P.boxes = (const rtb_box*)ctx->raw[RTB_BIND_BOXES];
+    P.toruses = (const rtb_torus*)ctx->raw[RTB_BIND_TORUSES]; P.rings = (const rtb_ring*)ctx->raw[RTB_BIND_RINGS];
+    P.lights_point = (const rtb_light_point*)ctx->raw[RTB_BIND_LIGHTS_POINT]; P.lights_direct = (const rtb_light_direct*)ctx->raw[RTB_BIND_LIGHTS_DIRECT];
+    P.lay = make_layout(d);
+    if (P.lay.total_bytes > ctx->packed_cap) {
+        if (ctx->packed) cudaFree(ctx->packed);
+        ctx->packed_cap = P.lay.total_bytes + 4096;
+        CU(cudaMalloc(&ctx->packed, ctx->packed_cap));
+        ctx->dirty = true;
+    }
+    P.packed = ctx->packed;
+    P.cube.base = ctx->cube; P.cube.w = ctx->cube_w; P.cube.h = ctx->cube_h;
+    for (int u = 1; u <= 5; u++) {
+        P.tex[u].base = ctx->tex[u].dev; P.tex[u].w = ctx->tex[u].w; P.tex[u].h = ctx->tex[u].h; P.tex[u].levels = ctx->tex[u].levels;
+        memcpy(P.tex[u].level_off, ctx->tex[u].off, sizeof ctx->tex[u].off);
+    }
+    P.fb = target; P.rank = ctx->rank; P.world = ctx->world; P.block_rows = ctx->block_rows; P.local_rows = ctx->local_rows;
+    P.tile_counter = ctx->tile_counter;
+    P.n_tiles_x = (ctx->width + 7) / 8; P.n_tiles_y = (ctx->local_rows + 3) / 4;
+    P.cull = ctx->opt_cull;
+    P.counters = counted ? ctx->counters : nullptr;
+
+    const bool strict = ctx->opt_strict != 0;
+    int kernel = ctx->opt_kernel;
+    const bool textured = scene_uses_textures(ctx);
+    if (kernel == RTB_KERNEL_AUTO) kernel = textured ? RTB_KERNEL_QUAD : RTB_KERNEL_PERSISTENT;
+    if (kernel == RTB_KERNEL_PERSISTENT && textured)
+        return fail(ctx, RTB_ERR_STATE, "the persistent kernel cannot render scenes that reference 2-D textures (textureNum != 0)");
+    const int launch_kernel = kernel == RTB_KERNEL_QUAD ? RTB_LAUNCH_QUAD : RTB_LAUNCH_PERSISTENT;
+    const int threads = kernel == RTB_KERNEL_QUAD ? QUAD_THREADS : PERSIST_THREADS;
+    const size_t smem = P.lay.total_bytes;
+    if (smem > 227 * 1024) return fail(ctx, RTB_ERR_INVALID, "packed scene (%zu bytes) exceeds the 227 KB shared-memory budget", smem);
+
+    int per_sm = 0;
+    int e = strict ? rtb_strict_occupancy(launch_kernel, smem, &per_sm) : rtb_fast_occupancy(launch_kernel, smem, &per_sm);
+    if (e || per_sm < 1) return fail(ctx, RTB_ERR_CUDA, "occupancy query failed (%s), smem %zu", cudaGetErrorString((cudaError_t)e), smem);
+    if (ctx->opt_ctas_per_sm > 0 && ctx->opt_ctas_per_sm < per_sm) per_sm = ctx->opt_ctas_per_sm;
+    const int grid = ctx->n_sm * per_sm;                 /* persistent: a whole number of CTAs on every one of the SMs */
+
+    if (st != ctx->stream) {                             /* uploads ran on the context stream: order them before this frame */
+        CU(cudaEventRecord(ctx->ev_upload, ctx->stream));
+        CU(cudaStreamWaitEvent(st, ctx->ev_upload, 0));
+    }
+    if (ctx->dirty) {
+        int pe = strict ? rtb_strict_launch_pack(&P, ctx->packed, st) : rtb_fast_launch_pack(&P, ctx->packed, st);
+        if (pe) return fail(ctx, RTB_ERR_CUDA, "pack kernel launch: %s", cudaGetErrorString((cudaError_t)pe));
+        ctx->dirty = false;
+    }
+    CU(cudaMemsetAsync(ctx->tile_counter, 0, sizeof(unsigned int), st));
+    if (counted) CU(cudaMemsetAsync(ctx->counters, 0, CNT_NUM * sizeof(unsigned long long), st));
+    if (timed) CU(cudaEventRecord(ctx->ev0, st));
+    e = strict ? rtb_strict_launch(&P, launch_kernel, counted ? 1 : 0, grid, threads, smem, st)
+               : rtb_fast_launch(&P, launch_kernel, counted ? 1 : 0, grid, threads, smem, st);
+    if (e) return fail(ctx, RTB_ERR_CUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+    if (timed) { CU(cudaEventRecord(ctx->ev1, st)); ctx->timed_pending = true; }
+    ctx->stats.kernel_used = kernel; ctx->stats.grid = grid; ctx->stats.block = threads; ctx->stats.smem_bytes = (int)smem;
+    return RTB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rtb_version(void) { return "rtb200 0.1 (sm_100a)"; }
+
+const char* rtb_last_error(const rtb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+rtb_ctx* rtb_create(int width, int height, int device) {
+    rtb_ctx* ctx = nullptr;
+    if (width <= 0 || height <= 0) { fail(nullptr, RTB_ERR_INVALID, "bad size %dx%d", width, height); return nullptr; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { fail(nullptr, RTB_ERR_NO_DEVICE, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e)); return nullptr; }
+    if (device < 0 || device >= n) { fail(nullptr, RTB_ERR_INVALID, "device %d out of range (%d devices)", device, n); return nullptr; }
+    ctx = new rtb_ctx();
+    ctx->device = device; ctx->width = width; ctx->height = height;
+    auto bail = [&](const char* what, cudaError_t err) { fail(nullptr, RTB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err)); rtb_destroy(ctx); return (rtb_ctx*)nullptr; };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (prop.major < 10) { fail(nullptr, RTB_ERR_NO_DEVICE, "device %s is sm_%d%d; this library carries sm_100a code only", prop.name, prop.major, prop.minor); rtb_destroy(ctx); return nullptr; }
+    ctx->n_sm = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_upload, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMalloc(&ctx->tile_counter, 256)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->counters, CNT_NUM * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
+    ctx->local_rows = height;
+    ctx->fb_floats = (size_t)width * height * 4;
+    if ((e = cudaMalloc(&ctx->fb, ctx->fb_floats * sizeof(float))) != cudaSuccess) return bail("cudaMalloc framebuffer", e);
+    return ctx;
+}
+
+void rtb_destroy(rtb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int b = 0; b < RTB_NUM_BINDINGS; b++) if (ctx->raw[b]) cudaFree(ctx->raw[b]);
+    if (ctx->packed) cudaFree(ctx->packed);
+    if (ctx->tile_counter) cudaFree(ctx->tile_counter);
+    if (ctx->counters) cudaFree(ctx->counters);
+    if (ctx->fb) cudaFree(ctx->fb);
+    if (ctx->cube) cudaFree(ctx->cube);
+    for (int u = 0; u < 6; u++) if (ctx->tex[u].dev) cudaFree(ctx->tex[u].dev);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_upload) cudaEventDestroy(ctx->ev_upload);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int rtb_set_partition(rtb_ctx* ctx, int rank, int world, int block_rows) {
+    if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "null context");
+    if (world < 1 || rank < 0 || rank >= world || block_rows < 4 || (block_rows & 3))
+        return fail(ctx, RTB_ERR_INVALID, "bad partition rank %d / world %d / block_rows %d (block_rows must be a multiple of 4)", rank, world, block_rows);
+    ctx->rank = rank; ctx->world = world; ctx->block_rows = block_rows;
+    ctx->local_rows = compute_local_rows(ctx->height, rank, world, block_rows);
+    return RTB_OK;
+}
+
+int rtb_local_rows(const rtb_ctx* ctx) { return ctx ? ctx->local_rows : 0; }
+
+int rtb_set_defines(rtb_ctx* ctx, const rtb_defines* d) {
+    if (!ctx || !d) return fail(ctx, RTB_ERR_INVALID, "null argument");
+    const int* c = &d->sphere_size;
+    for (int i = 0; i < 8; i++) if (c[i] < 0 || c[i] > (1 << 20)) return fail(ctx, RTB_ERR_INVALID, "count %d out of range: %d", i, c[i]);
+    if (d->iterations < 0) return fail(ctx, RTB_ERR_INVALID, "negative iterations");
+    ctx->defines = *d;
+    ctx->have_defines = true;
+    ctx->dirty = true;
+    return RTB_OK;
+}
+
+int rtb_upload(rtb_ctx* ctx, int binding, const void* data, size_t bytes) {
+    if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "null context");
+    if (binding < 0 || binding >= RTB_NUM_BINDINGS) return fail(ctx, RTB_ERR_INVALID, "unknown uniform-block binding %d", binding);
+    if (bytes % ELEM_SIZE[binding]) return fail(ctx, RTB_ERR_INVALID, "binding %d: %zu bytes is not a multiple of the %zu-byte element", binding, bytes, ELEM_SIZE[binding]);
+    CU(cudaSetDevice(ctx->device));
+    if (bytes > ctx->raw_cap[binding] || !ctx->raw[binding]) {
+        if (ctx->raw[binding]) { CU(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->raw[binding]); ctx->raw[binding] = nullptr; }
+        size_t cap = bytes < 256 ? 256 : bytes;
+        CU(cudaMalloc(&ctx->raw[binding], cap));
+        ctx->raw_cap[binding] = cap;
+    }
+    if (data && bytes) {
+        /* pageable source: the runtime stages it before returning, so the caller may reuse `data` at once */
+        CU(cudaMemcpyAsync(ctx->raw[binding], data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->shadow[binding].assign((const uint8_t*)data, (const uint8_t*)data + bytes);
+        ctx->raw_bytes[binding] = bytes;
+    } else if (bytes == 0) {
+        ctx->raw_bytes[binding] = 0;
+        ctx->shadow[binding].clear();
+    }   /* data == NULL with bytes > 0: allocation only (glBufferData(size, NULL)), contents arrive by a later upload */
+    ctx->dirty = true;
+    return RTB_OK;
+}
+
+int rtb_set_cubemap(rtb_ctx* ctx, const uint8_t* const faces[6], int w, int h, int channels) {
+    if (!ctx || !faces) return fail(ctx, RTB_ERR_INVALID, "null argument");
+    if (w <= 0 || h <= 0 || channels < 1 || channels > 4) return fail(ctx, RTB_ERR_INVALID, "bad cubemap %dx%dx%d", w, h, channels);
+    CU(cudaSetDevice(ctx->device));
+    size_t face_bytes = (size_t)w * h * 4;
+    std::vector<uint8_t> rgba(face_bytes * 6);
+    for (int f = 0; f < 6; f++) {
+        if (!faces[f]) return fail(ctx, RTB_ERR_INVALID, "cubemap face %d is null", f);
+        for (size_t i = 0; i < (size_t)w * h; i++) {
+            const uint8_t* s = faces[f] + i * channels;
+            uint8_t* o = rgba.data() + f * face_bytes + i * 4;
+            o[0] = s[0]; o[1] = channels >= 2 ? s[1] : 0; o[2] = channels >= 3 ? s[2] : 0; o[3] = channels == 4 ? s[3] : 255;
+        }
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->cube) { cudaFree(ctx->cube); ctx->cube = nullptr; }
+    CU(cudaMalloc(&ctx->cube, rgba.size()));
+    CU(cudaMemcpy(ctx->cube, rgba.data(), rgba.size(), cudaMemcpyHostToDevice));
+    ctx->cube_w = w; ctx->cube_h = h;
+    return RTB_OK;
+}
+
+int rtb_set_texture2d(rtb_ctx* ctx, int unit, const uint8_t* pixels, int w, int h, int channels) {
+    if (!ctx || !pixels) return fail(ctx, RTB_ERR_INVALID, "null argument");
+    if (unit < 1 || unit > 5) return fail(ctx, RTB_ERR_INVALID, "texture unit %d out of range 1..5", unit);
+    if (w <= 0 || h <= 0 || channels < 1 || channels > 4) return fail(ctx, RTB_ERR_INVALID, "bad texture %dx%dx%d", w, h, channels);
+    CU(cudaSetDevice(ctx->device));
+    std::vector<uint8_t> chain;
+    Tex2D t;
+    build_mip_chain(pixels, w, h, channels, chain, t);
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->tex[unit].dev) { cudaFree(ctx->tex[unit].dev); ctx->tex[unit].dev = nullptr; }
+    CU(cudaMalloc(&t.dev, chain.size()));
+    CU(cudaMemcpy(t.dev, chain.data(), chain.size(), cudaMemcpyHostToDevice));
+    ctx->tex[unit] = t;
+    return RTB_OK;
+}
+
+int rtb_set_option(rtb_ctx* ctx, const char* key, int value) {
+    if (!ctx || !key) return fail(ctx, RTB_ERR_INVALID, "null argument");
+    if (!strcmp(key, "kernel")) { if (value < 0 || value > 2) return fail(ctx, RTB_ERR_INVALID, "kernel must be 0..2"); ctx->opt_kernel = value; }
+    else if (!strcmp(key, "strict")) ctx->opt_strict = value ? 1 : 0;
+    else if (!strcmp(key, "cull")) ctx->opt_cull = value ? 1 : 0;
+    else if (!strcmp(key, "ctas_per_sm")) ctx->opt_ctas_per_sm = value;
+    else return fail(ctx, RTB_ERR_INVALID, "unknown option '%s'", key);
+    return RTB_OK;
+}
+
+int rtb_render(rtb_ctx* ctx) {
+    if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "null context");
+    return do_render(ctx, ctx->fb, ctx->stream, false, true);
+}
+
+int rtb_render_to(rtb_ctx* ctx, void* device_rgba32f, void* cuda_stream) {
+    if (!ctx || !device_rgba32f) return fail(ctx, RTB_ERR_INVALID, "null argument");
+    return do_render(ctx, (float*)device_rgba32f, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, false, cuda_stream == nullptr);
+}
+
+int rtb_sync(rtb_ctx* ctx) {
+    if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "null context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->timed_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.kernel_ms = ms;
+        ctx->timed_pending = false;
+    }
+    return RTB_OK;
+}
+
+int rtb_render_counted(rtb_ctx* ctx, rtb_stats* out) {
+    if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "null context");
+    int rc = do_render(ctx, ctx->fb, ctx->stream, true, false);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    unsigned long long c[CNT_NUM];
+    CU(cudaMemcpy(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost));
+    rtb_stats& s = ctx->stats;
+    const rtb_defines& d = ctx->defines;
+    s.pixels = c[CNT_PIXELS]; s.rays_nearest = c[CNT_RAYS_NEAREST]; s.rays_shadow = c[CNT_RAYS_SHADOW];
+    s.dk_iterations = c[CNT_DK]; s.light_evals = c[CNT_LIGHT_EVALS];
+    for (int i = 0; i < 7; i++) s.shaded_hits[i] = c[CNT_SHADED0 + i];
+    /* every scan tests every primitive of the classes it visits (rt.frag:587-658) */
+    const uint64_t rn = s.rays_nearest, rs = s.rays_shadow;
+    s.tests[RTB_TYPE_SPHERE] = (rn + rs) * d.sphere_size;   s.tests[RTB_TYPE_PLANE] = rn * d.plane_size;
+    s.tests[RTB_TYPE_SURFACE] = (rn + rs) * d.surface_size; s.tests[RTB_TYPE_BOX] = (rn + rs) * d.box_size;
+    s.tests[RTB_TYPE_TORUS] = (rn + rs) * d.torus_size;     s.tests[RTB_TYPE_RING] = (rn + rs) * d.ring_size;
+    s.tests[RTB_TYPE_POINT_LIGHT] = rn * d.light_point_size;
+    s.flops = algorithmic_flops(s);
+    if (out) *out = s;
+    return RTB_OK;
+}
+
+int rtb_get_stats(rtb_ctx* ctx, rtb_stats* out) {
+    if (!ctx || !out) return fail(ctx, RTB_ERR_INVALID, "null argument");
+    int rc = rtb_sync(ctx);
+    if (rc) return rc;
+    *out = ctx->stats;
+    return RTB_OK;
+}
+
+int rtb_read_rgba32f(rtb_ctx* ctx, float* dst) {
+    if (!ctx || !dst) return fail(ctx, RTB_ERR_INVALID, "null argument");
+    int rc = rtb_sync(ctx);
+    if (rc) return rc;
+    CU(cudaMemcpy(dst, ctx->fb, (size_t)ctx->local_rows * ctx->width * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+    return RTB_OK;
+}
+
+int rtb_read_rgba8(rtb_ctx* ctx, uint8_t* dst) {
+    if (!ctx || !dst) return fail(ctx, RTB_ERR_INVALID, "null argument");
+    size_t n = (size_t)ctx->local_rows * ctx->width * 4;
+    std::vector<float> tmp(n);
+    int rc = rtb_read_rgba32f(ctx, tmp.data());
+    if (rc) return rc;
+    for (size_t i = 0; i < n; i++) {
+        float v = tmp[i];
+        v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);        /* GL unorm8 conversion of the colour buffer; NaN -> 0 */
+        if (!(v == v)) v = 0.f;
+        dst[i] = (uint8_t)(v * 255.0f + 0.5f);
+    }
+    return RTB_OK;
+}
+
+void* rtb_device_framebuffer(rtb_ctx* ctx) { return ctx ? ctx->fb : nullptr; }
+
+}  // extern "C"
