@@ -7,6 +7,7 @@ alias module at the repository root.
   scene     rt_* structs + SceneManager / SurfaceFactory factories (src/scene.h, SceneManager.cpp, Surface.h)
   scenes    the reference's default scene and the synthetic BASELINE.json scenes
   textures  decoded sampler inputs
+  dist      row-block partition + the single frame gather (torch.distributed: NCCL / gloo)
   api       GLWrapper (src/GLWrapper.h) over the C-ABI of librtb200.so (CUDA, sm_100a; no CPU path)
 """
 from . import api, scene, scenes, textures  # noqa: F401

@@ -42,9 +42,10 @@ def load_assets(assets_dir: str, cubemap=DEFAULT_CUBEMAP, textures=DEFAULT_TEXTU
 
 
 def _hash2(x, y, seed):
-    h = (x.astype(np.uint32) * np.uint32(374761393) + y.astype(np.uint32) * np.uint32(668265263) + np.uint32(seed) * np.uint32(2246822519))
-    h = (h ^ (h >> np.uint32(13))) * np.uint32(1274126177)
-    return (h ^ (h >> np.uint32(16)))
+    m = np.uint64(0xFFFFFFFF)
+    h = (x.astype(np.uint64) * np.uint64(374761393) + y.astype(np.uint64) * np.uint64(668265263) + np.uint64(seed * 2246822519 & 0xFFFFFFFF)) & m
+    h = ((h ^ (h >> np.uint64(13))) * np.uint64(1274126177)) & m
+    return (h ^ (h >> np.uint64(16))).astype(np.uint32)
 
 
 def procedural_textures(cube_size=64, small=True) -> TextureSet:

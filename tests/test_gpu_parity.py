@@ -1,0 +1,277 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (librtb200.so), against the CPU oracle.
+
+Tolerance (BASELINE.json north_star): per-channel |CUDA - reference| <= 1e-4 on the RGBA32F framebuffer.
+  * strict build: EVERY pixel must satisfy it (observed <= 5e-7: + - * / sqrt are bit-identical to the oracle,
+    only libm's pow/exp/atan/asin/log2 differ by an ulp).
+  * fast build (FMA contraction etc.): ulp-level differences are amplified by every reflection off a curved
+    surface (chaotic paths), so the bound holds for all but a stated fraction of pixels at full bounce depth,
+    and for >= 99 % of pixels when paths are cut after the first hit.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import rtb200
+from oracle.binding import Oracle, Stats
+from rtb200 import scenes
+from rtb200.api import KERNEL_PERSISTENT, KERNEL_QUAD
+from rtb200.scene import SceneManager as SM
+from util import GOLDEN, golden_files, pixel_err, scene_from_npz
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def gpu_render(sc, ts, kernel=0, strict=1, cull=0, counted=False):
+    w, h = int(sc.scene["canvas_width"]), int(sc.scene["canvas_height"])
+    gl = rtb200.GLWrapper(w, h)
+    gl.init_window()
+    try:
+        rtb200.setup_scene(gl, sc, ts)
+        gl.set_option("kernel", kernel)
+        gl.set_option("strict", strict)
+        gl.set_option("cull", cull)
+        if counted:
+            st = gl.draw_counted()
+            return gl.read_pixels(), st
+        gl.draw()
+        return gl.read_pixels(), gl.stats()
+    finally:
+        gl.stop()
+
+
+CASES = {
+    "default256": lambda: scenes.build_config("default256"),                       # BASELINE configs[0], full size
+    "default1080/8": lambda: scenes.build_config("default1080", 1 / 8),
+    "spheres4k/12": lambda: scenes.build_config("spheres4k", 1 / 12),
+    "tori1080/8": lambda: scenes.build_config("tori1080", 1 / 8),
+    "mixed1024/16": lambda: scenes.build_config("mixed1024_4k", 1 / 16),
+    "mini4": lambda: scenes.synthetic_scene("mini4", 250, 130, 6),                 # canvas not a multiple of the 8x4 tile
+}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_strict_build_matches_oracle_on_every_pixel(case, procedural):
+    sc = CASES[case]()
+    ost = Stats()
+    want = Oracle(sc, procedural).render(stats=ost)
+    kernels = [KERNEL_QUAD] if sc.uses_textures() else [KERNEL_QUAD, KERNEL_PERSISTENT]
+    for k in kernels:
+        got, st = gpu_render(sc, procedural, kernel=k, strict=1, counted=True)
+        err = pixel_err(got, want)
+        assert err.max() <= TOL, f"{case} kernel {k}: {int((err > TOL).sum())} px beyond {TOL}, max {err.max()}"
+        assert st.kernel_used == k
+        o = ost.as_dict()
+        c = st.as_dict()
+        for key in ("pixels", "rays_nearest", "rays_shadow", "tests", "dk_iterations", "shaded_hits", "light_evals"):
+            assert o[key] == c[key], (case, k, key, o[key], c[key])       # same rays, same tests, same solver iterations
+
+
+@pytest.mark.parametrize("fname", [f for f in golden_files() if "default_tex" not in f])
+def test_strict_build_matches_reference_shader_golden_vectors(fname, procedural):
+    """tests/golden/*.npz were produced by the reference's own rt.frag (oracle/_ref)."""
+    z = np.load(os.path.join(GOLDEN, fname))
+    sc = scene_from_npz(z)
+    for k in (KERNEL_QUAD, KERNEL_PERSISTENT):
+        got, _ = gpu_render(sc, procedural, kernel=k)
+        err = pixel_err(got, z["image"])
+        assert err.max() <= TOL, f"{fname} kernel {k}: max {err.max()}"
+
+
+def test_textured_golden_vector_outside_diverged_quads(procedural):
+    """The textured fixture pairs derivatives by call ordinal (all oracle/_ref can observe); the quad kernel pairs by
+    program position.  They agree wherever the 2x2 quad did not diverge: compare through the oracle's two rules."""
+    z = np.load(os.path.join(GOLDEN, "default_tex_96x64_it3.npz"))
+    sc = scene_from_npz(z)
+    o = Oracle(sc, procedural)
+    prog = o.render()
+    got, _ = gpu_render(sc, procedural, kernel=KERNEL_QUAD)
+    assert pixel_err(got, prog).max() <= TOL
+    same_rule = pixel_err(prog, z["image"]) <= 2e-6
+    assert same_rule.mean() > 0.97
+    assert pixel_err(got, z["image"])[same_rule].max() <= TOL
+
+
+@pytest.mark.parametrize("case", ["spheres4k/12", "tori1080/8", "mixed1024/16", "default1080/8"])
+def test_fast_build_error_budget(case, procedural):
+    sc = CASES[case]()
+    want = Oracle(sc, procedural).render()
+    got, _ = gpu_render(sc, procedural, strict=0)
+    err = pixel_err(got, want)
+    frac = float((err > TOL).mean())
+    assert frac <= 0.15, f"{case}: {frac:.2%} of pixels beyond {TOL} at full depth"
+    assert float(np.median(err)) <= 1e-6
+    sc.scene["reflect_depth"] = 1                    # first hit only: no chaotic amplification
+    want1 = Oracle(sc, procedural).render()
+    got1, _ = gpu_render(sc, procedural, strict=0)
+    frac1 = float((pixel_err(got1, want1) > TOL).mean())
+    assert frac1 <= 0.01, f"{case}: {frac1:.3%} of first-hit pixels beyond {TOL}"
+
+
+def test_quad_and_persistent_kernels_are_bit_identical(procedural):
+    sc = scenes.build_config("mixed1024_4k", 1 / 10)
+    a, _ = gpu_render(sc, procedural, kernel=KERNEL_QUAD)
+    b, _ = gpu_render(sc, procedural, kernel=KERNEL_PERSISTENT)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    a, _ = gpu_render(sc, procedural, kernel=KERNEL_QUAD, strict=0)
+    b, _ = gpu_render(sc, procedural, kernel=KERNEL_PERSISTENT, strict=0)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_torus_cull_option_preserves_results(procedural):
+    sc = scenes.build_config("tori1080", 1 / 6)
+    a, _ = gpu_render(sc, procedural, cull=0)
+    b, _ = gpu_render(sc, procedural, cull=1)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+# ---------------------------------------------------------------- edge cases
+def test_empty_scene_is_sky_only(procedural):
+    sc = scenes._base(64, 40, 4)
+    sc.lights_point.clear()
+    sc.lights_direct.clear()
+    want = Oracle(sc, procedural).render()
+    for k in (KERNEL_QUAD, KERNEL_PERSISTENT):
+        got, _ = gpu_render(sc, procedural, kernel=k)
+        assert pixel_err(got, want).max() <= TOL
+    got, _ = gpu_render(sc, None)
+    assert np.array_equal(got[..., :3], np.zeros_like(got[..., :3])) and (got[..., 3] == 1).all()
+
+
+def test_zero_iterations_and_no_lights(procedural):
+    sc = scenes.synthetic_scene("mini1", 32, 20, 0)
+    got, _ = gpu_render(sc, procedural)
+    assert np.array_equal(got[..., :3], np.zeros_like(got[..., :3]))
+    sc = scenes.synthetic_scene("mini1", 32, 20, 3)
+    sc.lights_point.clear()
+    sc.lights_direct.clear()
+    want = Oracle(sc, procedural).render()
+    for k in (KERNEL_QUAD, KERNEL_PERSISTENT):
+        got, _ = gpu_render(sc, procedural, kernel=k)
+        assert pixel_err(got, want).max() <= TOL
+
+
+def test_glass_hollow_sphere_ring_and_rotated_camera(procedural):
+    sc = scenes.synthetic_scene("mini6", 96, 64, 5)
+    cm = SM.create_material
+    sc.spheres.append(SM.create_sphere((0, 2, -4), 1.5, cm((1, 1, 1), 200, 0.1, 1.125, (1, 0, 2), 1), True))     # glass, hollow
+    sc.spheres.append(SM.create_sphere((3, 2, -2), 1.0, cm((1, 1, 1), 50, 0.0, 1.5, (0.2, 0.5, 0.1), 1), False))  # glass, no mirror term
+    ring = SM.create_ring((-3, 3, 0), 1.0, 2.5, cm((0.8, 0.8, 0.3), 10, 0.0))
+    sc.rings.append(ring)
+    sc.lights_point.append(SM.create_light_point((-4, 6, -6, 0.5), (1, 0.8, 0.6), 12))
+    from rtb200.scene import quat_from_euler
+    sc.scene["quat_camera_rotation"] = quat_from_euler(0.15, -0.2, 0)
+    want = Oracle(sc, procedural).render()
+    for k in (KERNEL_QUAD, KERNEL_PERSISTENT):
+        got, _ = gpu_render(sc, procedural, kernel=k)
+        err = pixel_err(got, want)
+        assert err.max() <= TOL, (k, err.max(), int((err > TOL).sum()))
+
+
+def test_textured_ring_shadows_and_box_texture(procedural):
+    """fwidth / implicit-LOD sites, including alpha-accumulating ring shadows (rt.frag:644-651)."""
+    sc = scenes.default_scene(160, 90, 3)
+    sc.scene["camera_pos"] = (6, 2, -3)
+    ring = SM.create_ring((8, 3.5, 6), 0.5, 3.0, SM.create_material((0, 0, 0), 0, 0))
+    ring["textureNum"] = 4
+    from rtb200.scene import quat_angle_axis
+    ring["quat_rotation"] = quat_angle_axis(1.3, (1, 0, 0))
+    sc.rings.append(ring)
+    want = Oracle(sc, procedural).render()
+    got, st = gpu_render(sc, procedural)
+    assert st.kernel_used == KERNEL_QUAD
+    err = pixel_err(got, want)
+    assert err.max() <= TOL, (err.max(), int((err > TOL).sum()))
+
+
+def test_maximum_uniform_block_population(procedural):
+    """585 spheres = the most a 64 KB GL uniform block holds."""
+    sc = scenes._base(64, 36, 2)
+    rng = scenes.PCG32(9)
+    scenes._add_spheres(sc, rng, 585)
+    want = Oracle(sc, procedural).render()
+    got, _ = gpu_render(sc, procedural)
+    assert pixel_err(got, want).max() <= TOL
+
+
+# ---------------------------------------------------------------- error behaviour
+def test_call_order_and_argument_errors(procedural):
+    gl = rtb200.GLWrapper(32, 32)
+    gl.init_window()
+    with pytest.raises(rtb200.RtbError, match="init_shaders|set_defines"):
+        gl.draw()
+    sc = scenes.default_scene(32, 32, 1)
+    rtb200.setup_scene(gl, sc, procedural)
+    gl.set_option("kernel", KERNEL_PERSISTENT)
+    with pytest.raises(rtb200.RtbError, match="2-D textures"):
+        gl.draw()
+    with pytest.raises(rtb200.RtbError, match="unknown option"):
+        gl.set_option("bogus", 1)
+    with pytest.raises(rtb200.RtbError, match="partition"):
+        gl.set_partition(3, 2, 16)
+    gl.stop()
+    gl = rtb200.GLWrapper(32, 32)
+    gl.init_window()
+    sc = scenes.synthetic_scene("mini1", 64, 64, 1)          # canvas size differs from the context's
+    rtb200.setup_scene(gl, sc, procedural)
+    with pytest.raises(rtb200.RtbError, match="canvas"):
+        gl.draw()
+    gl.stop()
+
+
+# ---------------------------------------------------------------- full BASELINE sizes: size-independent properties
+def _render_partitioned(sc, ts, world, strict=1):
+    w, h = int(sc.scene["canvas_width"]), int(sc.scene["canvas_height"])
+    parts = []
+    for r in range(world):
+        gl = rtb200.GLWrapper(w, h)
+        gl.init_window()
+        gl.set_partition(r, world, 16)
+        rtb200.setup_scene(gl, sc, ts)
+        gl.set_option("strict", strict)
+        gl.draw()
+        parts.append(gl.read_pixels())
+        gl.stop()
+    return rtb200.gather_rows(parts, h, world, 16)
+
+
+def test_full_size_4k_mixed1024_properties(procedural):
+    """BASELINE configs[4] scene at the headline 3840x2160 / 8 bounces."""
+    sc = scenes.build_config("mixed1024_4k")
+    full, st = gpu_render(sc, procedural, kernel=KERNEL_PERSISTENT)
+    assert full.shape == (2160, 3840, 4) and np.isfinite(full).all() and (full[..., 3] == 1).all()
+    again, _ = gpu_render(sc, procedural, kernel=KERNEL_PERSISTENT)
+    assert np.array_equal(full.view(np.uint32), again.view(np.uint32))              # idempotent / deterministic
+    tiled = _render_partitioned(sc, procedural, 8)
+    assert np.array_equal(full.view(np.uint32), tiled.view(np.uint32))              # N-GPU tiling is bit-invariant
+    rng = np.random.default_rng(0)                                                  # sampled quads against the oracle
+    qx = (rng.integers(0, 3840 // 2, 1500) * 2).astype(np.int32)
+    qy = (rng.integers(0, 2160 // 2, 1500) * 2).astype(np.int32)
+    want = Oracle(sc, procedural).render_quads(qx, qy)
+    got = np.stack([full[qy, qx], full[qy, qx + 1], full[qy + 1, qx], full[qy + 1, qx + 1]], axis=1)
+    err = pixel_err(got, want)
+    assert err.max() <= TOL, (err.max(), int((err > TOL).sum()))
+
+
+def test_full_size_default1080_and_spheres4k_sampled(procedural):
+    for cfg, n in (("default1080", 3000), ("spheres4k", 3000), ("tori1080", 1500)):
+        sc = scenes.build_config(cfg)
+        w, h = int(sc.scene["canvas_width"]), int(sc.scene["canvas_height"])
+        full, _ = gpu_render(sc, procedural)
+        rng = np.random.default_rng(1)
+        qx = (rng.integers(0, w // 2, n) * 2).astype(np.int32)
+        qy = (rng.integers(0, h // 2, n) * 2).astype(np.int32)
+        want = Oracle(sc, procedural).render_quads(qx, qy)
+        got = np.stack([full[qy, qx], full[qy, qx + 1], full[qy + 1, qx], full[qy + 1, qx + 1]], axis=1)
+        err = pixel_err(got, want)
+        assert err.max() <= TOL, (cfg, err.max(), int((err > TOL).sum()))
+
+
+def test_full_size_8k_partition_invariance(procedural):
+    """BASELINE configs[4]: 7680x4320 tiled over 8 ranks equals the single-GPU frame bit for bit."""
+    sc = scenes.build_config("mixed1024_8k")
+    sc.scene["reflect_depth"] = 2                    # keeps the test short; tiling does not depend on depth
+    full, _ = gpu_render(sc, procedural)
+    tiled = _render_partitioned(sc, procedural, 8)
+    assert np.array_equal(full.view(np.uint32), tiled.view(np.uint32))
