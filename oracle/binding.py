@@ -35,7 +35,7 @@ class _Desc(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("pixels", C.c_uint64), ("rays_nearest", C.c_uint64), ("rays_shadow", C.c_uint64), ("tests", C.c_uint64 * 7),
-                ("dk_iterations", C.c_uint64), ("shaded_hits", C.c_uint64 * 7), ("light_evals", C.c_uint64)]
+                ("dk_iterations", C.c_uint64), ("shaded_hits", C.c_uint64 * 7), ("light_evals", C.c_uint64), ("dk_hist", C.c_uint64 * 61)]
 
     def as_dict(self):
         return {"pixels": self.pixels, "rays_nearest": self.rays_nearest, "rays_shadow": self.rays_shadow,

@@ -143,6 +143,7 @@ struct QuadCtx {
 
 struct Stats {
     uint64_t rays_nearest = 0, rays_shadow = 0, tests[7] = { 0 }, dk = 0, shaded[7] = { 0 }, light_evals = 0;
+    uint64_t dk_hist[61] = { 0 };
 };
 
 /* ---------------- one fragment-shader invocation ---------------- */
@@ -371,7 +372,7 @@ struct Frag {
             if (e < eps) break;
         }
         last_dk = iters;
-        if (st) st->dk += iters;
+        if (st) { st->dk += iters; st->dk_hist[iters]++; }
         vec4 rs = { c0.x, c1.x, c2.x, c3.x };
         vec4 ri = { fabsf(c0.y), fabsf(c1.y), fabsf(c2.y), fabsf(c3.y) };
         if (ri.x > eps || rs.x < 0.f) rs.x = 10000.f;
@@ -712,6 +713,7 @@ void add_stats(orc_stats* dst, const Stats& s, uint64_t pixels) {
     for (int i = 0; i < 7; i++) { dst->tests[i] += s.tests[i]; dst->shaded_hits[i] += s.shaded[i]; }
     dst->dk_iterations += s.dk;
     dst->light_evals += s.light_evals;
+    for (int i = 0; i <= 60; i++) dst->dk_hist[i] += s.dk_hist[i];
 }
 
 /* Run the four invocations of one 2x2 quad to the derivative fixed point (pin Q9). */
@@ -747,6 +749,7 @@ void render_quad(const Scene& S, int qx, int qy, float* out4x4, Stats* stats) {
         stats->rays_nearest += last.rays_nearest; stats->rays_shadow += last.rays_shadow; stats->dk += last.dk;
         stats->light_evals += last.light_evals;
         for (int i = 0; i < 7; i++) { stats->tests[i] += last.tests[i]; stats->shaded[i] += last.shaded[i]; }
+        for (int i = 0; i <= 60; i++) stats->dk_hist[i] += last.dk_hist[i];
     }
     for (int l = 0; l < 4; l++) { out4x4[l * 4 + 0] = col[l].x; out4x4[l * 4 + 1] = col[l].y; out4x4[l * 4 + 2] = col[l].z; out4x4[l * 4 + 3] = col[l].w; }
 }

@@ -42,6 +42,7 @@ typedef struct orc_stats {             /* same meaning as rtb_stats in include/r
     uint64_t dk_iterations;
     uint64_t shaded_hits[7];
     uint64_t light_evals;
+    uint64_t dk_hist[61];              /* histogram of Durand-Kerner iterations per (ray, torus) solve, index = k */
 } orc_stats;
 
 typedef struct orc_handle orc_handle;

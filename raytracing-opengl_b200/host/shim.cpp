@@ -1,0 +1,58 @@
+/* shim.cpp — headless GLFW + the three raw GL calls of the reference's application code. */
+#include <glad/glad.h>
+#include <GLFW/glfw3.h>
+#include "GLWrapper.h"
+#include "shim_state.h"
+
+struct GLFWwindow {
+    GLWrapper* owner = nullptr;
+    void* user = nullptr;
+    int frames_left = 1;
+    int should_close = 0;
+    GLFWcursorposfun cursor_cb = nullptr;
+    GLFWkeyfun key_cb = nullptr;
+    GLFWframebuffersizefun fb_cb = nullptr;
+};
+
+namespace {
+long g_frames_presented = 0;
+GLenum g_active_unit = GL_TEXTURE0;
+GLuint g_bound_2d[8] = { 0 };
+}
+
+GLFWwindow* rtb_shim_create_window(GLWrapper* owner, int frames) {
+    GLFWwindow* w = new GLFWwindow();
+    w->owner = owner;
+    w->frames_left = frames < 1 ? 1 : frames;
+    return w;
+}
+void rtb_shim_destroy_window(GLFWwindow* w) { delete w; }
+
+extern "C" {
+
+double glfwGetTime(void) { return (double)g_frames_presented / 60.0; }     /* deterministic 60 Hz clock */
+void glfwPollEvents(void) {}
+void glfwSwapInterval(int) {}
+void glfwSwapBuffers(GLFWwindow* w) {
+    if (w && w->owner) w->owner->present();
+    g_frames_presented++;
+    if (w && --w->frames_left <= 0) w->should_close = 1;
+}
+int glfwWindowShouldClose(GLFWwindow* w) { return w ? w->should_close : 1; }
+void glfwSetWindowShouldClose(GLFWwindow* w, int v) { if (w) w->should_close = v; }
+void glfwSetWindowUserPointer(GLFWwindow* w, void* p) { if (w) w->user = p; }
+void* glfwGetWindowUserPointer(GLFWwindow* w) { return w ? w->user : nullptr; }
+GLFWcursorposfun glfwSetCursorPosCallback(GLFWwindow* w, GLFWcursorposfun cb) { GLFWcursorposfun o = w->cursor_cb; w->cursor_cb = cb; return o; }
+GLFWkeyfun glfwSetKeyCallback(GLFWwindow* w, GLFWkeyfun cb) { GLFWkeyfun o = w->key_cb; w->key_cb = cb; return o; }
+GLFWframebuffersizefun glfwSetFramebufferSizeCallback(GLFWwindow* w, GLFWframebuffersizefun cb) { GLFWframebuffersizefun o = w->fb_cb; w->fb_cb = cb; return o; }
+void glfwSetInputMode(GLFWwindow*, int, int) {}
+
+/* main.cpp:178-187 re-binds the five 2-D textures to units 1..5 every frame; the unit of each texture was
+ * already fixed by load_texture(texNum, ...), so the calls only need to be accepted. */
+void glActiveTexture(GLenum texture) { g_active_unit = texture; }
+void glBindTexture(GLenum target, GLuint texture) {
+    if (target == GL_TEXTURE_2D && g_active_unit >= GL_TEXTURE0 && g_active_unit < GL_TEXTURE0 + 8) g_bound_2d[g_active_unit - GL_TEXTURE0] = texture;
+}
+void glViewport(GLint, GLint, GLsizei, GLsizei) {}
+
+}  // extern "C"
