@@ -62,14 +62,24 @@ def test_default_scene_matches_main_cpp():
     assert scenes.default_scene(63, 31).scene["canvas_width"] == 64       # odd sizes are bumped (main.cpp:40-41)
 
 
-@pytest.mark.skipif(not os.path.isfile(os.path.join(os.path.dirname(__file__), "golden", "default_scene_t0.npz")),
-                    reason="dump of the unchanged main.cpp run not generated yet")
+def _fields(arr):
+    out = []
+    for n in arr.dtype.names:
+        out += _fields(arr[n]) if arr[n].dtype.names else [np.asarray(arr[n], dtype=np.float64).ravel()]
+    return out
+
+
 def test_default_scene_equals_the_dump_of_the_unchanged_main_cpp():
-    """tests/golden/default_scene_t0.npz = the uniform buffers uploaded by the reference's own main.cpp through host/GLWrapper."""
+    """tests/golden/default_scene_t0.npz = the uniform buffers the reference's OWN main.cpp + SceneManager.cpp uploaded for
+    their first frame when run, unchanged, through host/GLWrapper (rt_headless on the B200 box, RT_DUMP_DIR)."""
+    from rtb200 import scene as S
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "default_scene_t0.npz"))
     sc = scenes.default_scene(int(z["width"]), int(z["height"]))
-    for name in ("spheres", "surfaces", "boxes", "toruses", "rings", "lights_point", "lights_direct"):
-        got = np.frombuffer(sc.array(name).tobytes(), dtype=np.float32)
-        want = np.frombuffer(z[name].tobytes(), dtype=np.float32)
-        assert got.shape == want.shape, name
-        assert np.allclose(got, want, rtol=2e-7, atol=1e-30, equal_nan=True), name
+    for name, dt in (("spheres", S.rt_sphere), ("surfaces", S.rt_surface), ("boxes", S.rt_box), ("toruses", S.rt_torus), ("rings", S.rt_ring),
+                     ("lights_point", S.rt_light_point), ("lights_direct", S.rt_light_direct)):
+        want = np.frombuffer(z[name].tobytes(), dtype=dt)
+        a, b = np.concatenate(_fields(sc.array(name))), np.concatenate(_fields(want))
+        assert a.shape == b.shape, name
+        assert np.allclose(a, b, rtol=3e-7, atol=1e-30), name
+    scene = np.frombuffer(z["scene"].tobytes(), dtype=S.rt_scene)[0]
+    assert np.allclose(scene["quat_camera_rotation"], sc.scene["quat_camera_rotation"]) and np.allclose(scene["camera_pos"], sc.scene["camera_pos"])
