@@ -39,4 +39,5 @@ def pixel_err(a, b):
 
 
 def golden_files():
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    """Image fixtures produced by oracle/_ref (default_scene_t0.npz is a scene dump, not an image fixture)."""
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and f != "default_scene_t0.npz")
