@@ -7,6 +7,9 @@
 
 #define QUAD_THREADS 128
 #define PERSIST_THREADS 128
+#ifndef PERSIST_MIN_BLOCKS
+#define PERSIST_MIN_BLOCKS 4
+#endif
 #define RTB_LAUNCH_QUAD 1
 #define RTB_LAUNCH_PERSISTENT 2
 

@@ -26,7 +26,7 @@ enum { JOB_MAIN = 0, JOB_SUB = 1, JOB_SHADOW = 2 };
 enum { COMB_REFRACT_SUB = 0, COMB_REFLECT = 1, COMB_DIFFUSE = 2 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(PERSIST_THREADS) persistent_kernel(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persistent_kernel(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar;
     stage_scene_tma(smem, &mbar, P.packed, P.lay.total_bytes);
