@@ -19,7 +19,7 @@ import numpy as np
 from .scene import UBO_BLOCKS, rt_defines
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtb200.so")
+LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "librtb200.so")     # RTB200_LIB: development builds only
 
 KERNEL_AUTO, KERNEL_QUAD, KERNEL_PERSISTENT = 0, 1, 2
 

@@ -53,7 +53,7 @@ DEV void flush_counters(const FrameParams& P, const Counters& c) {
         if ((threadIdx.x & 31) == 0 && s) atomicAdd(P.counters + slot, s);
     };
     red(c.rays_n, CNT_RAYS_NEAREST); red(c.rays_s, CNT_RAYS_SHADOW); red(c.dk, CNT_DK); red(c.light_evals, CNT_LIGHT_EVALS);
-    red(c.pixels, CNT_PIXELS); red(c.dk_fallback, CNT_DK_FALLBACK); red(c.dk_solves, CNT_DK_SOLVES);
+    red(c.pixels, CNT_PIXELS);
     for (int i = 0; i < 7; i++) red(c.shaded[i], CNT_SHADED0 + i);
 }
 

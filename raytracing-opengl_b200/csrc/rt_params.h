@@ -67,7 +67,7 @@ struct FrameParams {
 
 enum CounterSlot {
     CNT_RAYS_NEAREST = 0, CNT_RAYS_SHADOW = 1, CNT_TESTS0 = 2 /* ..8 */, CNT_DK = 9, CNT_SHADED0 = 10 /* ..16 */,
-    CNT_LIGHT_EVALS = 17, CNT_PIXELS = 18, CNT_DK_FALLBACK = 19, CNT_DK_SOLVES = 20, CNT_NUM = 21
+    CNT_LIGHT_EVALS = 17, CNT_PIXELS = 18, CNT_NUM = 19
 };
 
 #endif

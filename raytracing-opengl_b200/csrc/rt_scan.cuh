@@ -14,7 +14,7 @@
 
 namespace RTB_NS {
 
-struct Counters { unsigned rays_n, rays_s, dk, light_evals, pixels, dk_fallback, dk_solves; unsigned shaded[7]; };
+struct Counters { unsigned rays_n, rays_s, dk, light_evals, pixels; unsigned shaded[7]; };
 
 DEV int make_id(int type, int num) { return (type << 24) | num; }
 DEV int id_type(int id) { return id >> 24; }
@@ -89,9 +89,8 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
             TorusState st;
             if (torus_setup(ro, rd, S.tori + i, P.cull, st)) {
                 int iters;
-                bool fell_back = false;
-                t = torus_solve(st, iters, fell_back);
-                if (COUNT) { cnt.dk += iters; cnt.dk_solves++; if (fell_back) cnt.dk_fallback++; }
+                t = torus_solve(st, iters);
+                if (COUNT) cnt.dk += iters;
                 if (t > 0 && t < 100 && t < tmin) {
                     if (shadow_mode) shadow = 1.f; else { tmin = t; id = make_id(RTB_TYPE_TORUS, i); }
                 }

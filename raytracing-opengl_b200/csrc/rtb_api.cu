@@ -433,7 +433,6 @@ int rtb_render_counted(rtb_ctx* ctx, rtb_stats* out) {
     s.tests[RTB_TYPE_TORUS] = (rn + rs) * d.torus_size;     s.tests[RTB_TYPE_RING] = (rn + rs) * d.ring_size;
     s.tests[RTB_TYPE_POINT_LIGHT] = rn * d.light_point_size;
     s.flops = algorithmic_flops(s);
-    if (getenv("RTB_DEBUG_COUNTERS")) fprintf(stderr, "dk solves %llu, guarded-division fallbacks %llu\n", c[CNT_DK_SOLVES], c[CNT_DK_FALLBACK]);
     if (out) *out = s;
     return RTB_OK;
 }
