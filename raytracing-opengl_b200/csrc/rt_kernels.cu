@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(QUAD_THREADS) quad_kernel(const __grid_constan
 
         while (__any_sync(FULL, alive)) {                   /* one loop trip of rt.frag:821, all lanes together */
             float tm, sh_unused; int id; vec2 ruv;
-            scan_scene<COUNT, true>(P, S, ro, rd, alive, false, MAX_DIST, 0, tm, id, sh_unused, ruv, *cp);
+            scan_scene<COUNT, true, true>(P, S, ro, rd, alive, false, MAX_DIST, 0, tm, id, sh_unused, ruv, *cp);
             bool hit = alive && tm < MAX_DIST;
             if (alive && !hit) {                            /* rt.frag:892-895 */
                 color = color + texture_cube(P.cube, rd) * mask;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(QUAD_THREADS) quad_kernel(const __grid_constan
             Material mat2 = {}; vec3 n2 = mk3(0.f, 0.f, 0.f); vec3 spt2 = sro;
             if (__any_sync(FULL, sub)) {
                 float t2; int id2; vec2 ruv2;
-                scan_scene<COUNT, true>(P, S, sro, srd, sub, false, MAX_DIST, 1, t2, id2, sh_unused, ruv2, *cp);
+                scan_scene<COUNT, true, true>(P, S, sro, srd, sub, false, MAX_DIST, 1, t2, id2, sh_unused, ruv2, *cp);
                 bool sub_light = sub && id2 >= 0 && id_type(id2) == RTB_TYPE_POINT_LIGHT;
                 bool hit2 = sub && !sub_light && t2 < MAX_DIST;
                 vec3 pt2 = sro + srd * t2;
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(QUAD_THREADS) quad_kernel(const __grid_constan
                 for (int l = 0; l < n_lights; l++) {
                     LightSample L = light_sample(P, l, s_pt);
                     float tdummy, shadow; int iddummy; vec2 uvdummy;
-                    scan_scene<COUNT, true>(P, S, s_pt, L.dir_n, do_shade, true, L.dist, sub_shade ? 1 : 0, tdummy, iddummy, shadow, uvdummy, *cp);
+                    scan_scene<COUNT, true, true>(P, S, s_pt, L.dir_n, do_shade, true, L.dist, sub_shade ? 1 : 0, tdummy, iddummy, shadow, uvdummy, *cp);
                     if (do_shade) {
                         if (COUNT) cp->light_evals++;
                         shade_light(P, L, shadow, s_rd, s_col, s_dif, s_spec, s_n, diffuse, specular);
@@ -216,7 +216,6 @@ __global__ void pack_kernel(const FrameParams P, uint8_t* dst) {
     const int tid = threadIdx.x, nt = blockDim.x;
     PPlane* planes = (PPlane*)(dst + P.lay.off_plane);
     PSphere* spheres = (PSphere*)(dst + P.lay.off_sphere);
-    uint32_t* hollow = (uint32_t*)(dst + P.lay.off_hollow);
     PSurf* surfs = (PSurf*)(dst + P.lay.off_surf);
     PBox* boxes = (PBox*)(dst + P.lay.off_box);
     PTorus* tori = (PTorus*)(dst + P.lay.off_torus);
@@ -229,13 +228,9 @@ __global__ void pack_kernel(const FrameParams P, uint8_t* dst) {
     }
     for (int i = tid; i < P.n_sphere; i += nt) {
         const rtb_sphere& s = P.spheres[i];
-        PSphere p = { s.obj[0], s.obj[1], s.obj[2], s.obj[3] * s.obj[3] };
+        float r2 = s.obj[3] * s.obj[3];                      /* >= +0 (or NaN): the sign bit is free to carry `hollow` */
+        PSphere p = { s.obj[0], s.obj[1], s.obj[2], s.hollow != 0 ? __int_as_float(__float_as_int(r2) | 0x80000000) : r2 };
         spheres[i] = p;
-    }
-    for (int w = tid; w < (P.n_sphere + 31) / 32; w += nt) {
-        uint32_t bits = 0;
-        for (int b = 0; b < 32 && w * 32 + b < P.n_sphere; b++) if (P.spheres[w * 32 + b].hollow != 0) bits |= 1u << b;
-        hollow[w] = bits;
     }
     for (int i = tid; i < P.n_surf; i += nt) {
         const rtb_surface& s = P.surfaces[i];

@@ -6,10 +6,15 @@
 #include "rt_params.h"
 
 #define QUAD_THREADS 128
-#define PERSIST_THREADS 128
-#ifndef PERSIST_MIN_BLOCKS
-#define PERSIST_MIN_BLOCKS 4
+/* persistent kernel: ONE 16-warp CTA per SM (all warps share one staged scene and, while the frame drains, one job pool) */
+#ifndef PERSIST_THREADS
+#define PERSIST_THREADS 512
 #endif
+#ifndef PERSIST_MIN_BLOCKS
+#define PERSIST_MIN_BLOCKS 1
+#endif
+/* dynamic shared memory of the persistent kernel: staged scene (rounded up to 128 B) + one 32-B job and one 32-B result per thread */
+#define PERSIST_SMEM_BYTES(scene_bytes) ((((size_t)(scene_bytes) + 127u) & ~(size_t)127u) + (size_t)PERSIST_THREADS * 64u)
 #define RTB_LAUNCH_QUAD 1
 #define RTB_LAUNCH_PERSISTENT 2
 

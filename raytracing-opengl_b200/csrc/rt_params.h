@@ -17,7 +17,7 @@
 #include <stdint.h>
 #include "../../include/rtb200_types.h"
 
-struct PSphere { float cx, cy, cz, r2; };                                   /* 16 B; hollow flags in a side bitmask */
+struct PSphere { float cx, cy, cz, r2; };                                   /* 16 B; r2 = r*r, its SIGN BIT set for a hollow sphere */
 struct PPlane  { float nx, ny, nz, _0, px, py, pz, _1; };                    /* 32 B */
 struct PBox    { float qx, qy, qz, qw, px, py, pz, fx, fy, fz; int32_t tex; int32_t _0; };      /* 48 B */
 struct PTorus  { float qx, qy, qz, qw, px, py, pz, R2, r2, _0, _1, _2; };    /* 48 B */
@@ -27,7 +27,7 @@ struct PLight  { float x, y, z, r2; };                                       /* 
 
 /* byte offsets of each section inside the packed block (all multiples of 16) */
 struct PackedLayout {
-    uint32_t off_plane, off_sphere, off_hollow, off_surf, off_box, off_torus, off_ring, off_light;
+    uint32_t off_plane, off_sphere, off_surf, off_box, off_torus, off_ring, off_light;
     uint32_t total_bytes;
 };
 

@@ -19,18 +19,30 @@
  */
 #pragma once
 #include "rt_scan.cuh"
+#ifndef RTB_PERSIST_GATE
+#define RTB_PERSIST_GATE true
+#endif
 
 namespace RTB_NS {
 
 enum { JOB_MAIN = 0, JOB_SUB = 1, JOB_SHADOW = 2 };
 enum { COMB_REFRACT_SUB = 0, COMB_REFLECT = 1, COMB_DIFFUSE = 2 };
 
+/* Drain area in shared memory (behind the staged scene): one job and one result slot per thread. */
+struct DrainJob { float ro[3], rd[3], limit; int shadow; };             /* 32 B */
+struct DrainResult { float tm; int id; float shadow, u, v; int _pad[3]; };   /* 32 B */
+
 template <bool COUNT>
 __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persistent_kernel(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar;
-    stage_scene_tma(smem, &mbar, P.packed, P.lay.total_bytes);
+    __shared__ volatile int drain_flag;
+    __shared__ int n_jobs[2], next_job[2];
+    if (threadIdx.x == 0) { drain_flag = 0; n_jobs[0] = n_jobs[1] = 0; next_job[0] = next_job[1] = 0; }
+    stage_scene_tma(smem, &mbar, P.packed, P.lay.total_bytes);          /* contains the __syncthreads that publishes the zeros above */
     const SceneView S = make_view(smem, P.lay);
+    DrainJob* const jobs = (DrainJob*)(smem + ((P.lay.total_bytes + 127u) & ~127u));
+    DrainResult* const results = (DrainResult*)(jobs + PERSIST_THREADS);
 
     const int lane = threadIdx.x & 31;
     const unsigned total = (unsigned)(P.n_tiles_x * P.n_tiles_y) * 32u;
@@ -52,6 +64,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
     float cs = 0.f;
     bool cont = false;
     bool exhausted = false;
+    int parity = 0;
 
     for (;;) {
         /* ---- refill idle lanes with fresh pixels ---- */
@@ -81,14 +94,56 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
                     }
                 }
             }
-            if (base + (unsigned)__popc(want) >= total) exhausted = true;   /* warp-uniform: the counter passed the last pixel */
+            if (base + (unsigned)__popc(want) >= total) { exhausted = true; drain_flag = 1; }   /* warp-uniform: the counter passed the last pixel */
         }
+        if (drain_flag) exhausted = true;                       /* some warp of this CTA saw the end of the frame: no more refills */
         const bool active = px >= 0;
-        if (!__any_sync(FULL, active)) { if (exhausted) break; else continue; }
-
-        /* ---- one unified scene scan: each lane its own ray and mode ---- */
         float tm, shadow; int id; vec2 ruv;
-        scan_scene<COUNT, false>(P, S, jro, jrd, active, job == JOB_SHADOW, jlimit, 0, tm, id, shadow, ruv, cnt);
+
+        if (!exhausted) {
+            if (!__any_sync(FULL, active)) continue;
+            /* ---- steady state: one unified scene scan per warp, each lane its own ray and mode ---- */
+            scan_scene<COUNT, false, RTB_PERSIST_GATE>(P, S, jro, jrd, active, job == JOB_SHADOW, jlimit, 0, tm, id, shadow, ruv, cnt);
+        } else {
+            /* ---- drain: the frame has no fresh pixels left, lanes fall idle one by one.  All warps of the CTA pool
+             * the scans of their live paths in shared memory and serve them one ray per warp (coop_scan), so the
+             * SM stays busy until its last path ends instead of running full-length scans for a few lanes. ---- */
+            int slot = -1;
+            if (active) {
+                slot = atomicAdd(&n_jobs[parity], 1);
+                DrainJob j = { { jro.x, jro.y, jro.z }, { jrd.x, jrd.y, jrd.z }, jlimit, job == JOB_SHADOW ? 1 : 0 };
+                jobs[slot] = j;
+            }
+            __syncthreads();
+            const int n = n_jobs[parity];
+            if (n == 0) break;                                  /* CTA-uniform: every path of this CTA has ended */
+            if (threadIdx.x == 0) { n_jobs[parity ^ 1] = 0; next_job[parity ^ 1] = 0; }   /* nobody touches the other set before the next barrier */
+            for (;;) {
+                int j = 0;
+                if (lane == 0) j = atomicAdd(&next_job[parity], 1);
+                j = __shfl_sync(FULL, j, 0);
+                if (j >= n) break;
+                const DrainJob J = jobs[j];                     /* broadcast loads */
+                const vec3 bro = mk3(J.ro[0], J.ro[1], J.ro[2]), brd = mk3(J.rd[0], J.rd[1], J.rd[2]);
+                float r_tm, r_sh; int r_id; vec2 r_uv;
+                const unsigned dk_before = cnt.dk;
+                if (coop_scan<COUNT>(P, S, bro, brd, J.shadow != 0, J.limit, r_tm, r_id, r_sh, r_uv, cnt)) {
+                    /* a degenerate quadric makes the result depend on the scan order: redo this ray the serial way, on lane 0 */
+                    cnt.dk = dk_before;
+                    Counters scratch = {};
+                    scan_scene<COUNT, false, true>(P, S, bro, brd, lane == 0, J.shadow != 0, J.limit, 0, r_tm, r_id, r_sh, r_uv, scratch);
+                    if (COUNT) cnt.dk += scratch.dk;
+                }
+                if (lane == 0) { DrainResult r = { r_tm, r_id, r_sh, r_uv.x, r_uv.y, { 0, 0, 0 } }; results[j] = r; }
+            }
+            __syncthreads();
+            parity ^= 1;
+            if (active) {
+                const DrainResult r = results[slot];
+                tm = r.tm; id = r.id; shadow = r.shadow; ruv = mk2(r.u, r.v);
+                if (COUNT) { if (job == JOB_SHADOW) cnt.rays_s++; else cnt.rays_n++; }
+            }
+        }
         if (!active) continue;
 
         /* ---- per-lane post-processing ---- */

@@ -42,8 +42,11 @@ DEV Derivs quad_derivs(bool site, int tag, vec2 uv) {
 
 /* TEX: 2-D textures may be referenced (quad kernel): textured rings add their alpha to
  * the shadow term (rt.frag:644-651) and need the quad exchange -> scan_scene must then be
- * called from warp-uniform control flow.  ctx = 0 main path / 1 getReflectedColor. */
-template <bool COUNT, bool TEX>
+ * called from warp-uniform control flow.  ctx = 0 main path / 1 getReflectedColor.
+ * GATE: lanes with active == false skip the tests (quad kernel: dead paths and helper lanes are common).
+ * The persistent kernel passes GATE = false: idle lanes exist only while the frame drains, they re-scan their
+ * last ray and the result is dropped, which saves a branch region per primitive. */
+template <bool COUNT, bool TEX, bool GATE>
 DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, bool active, bool shadow_mode, float limit, int ctx,
                     float& tmin_out, int& id_out, float& shadow_out, vec2& ring_uv_out, Counters& cnt) {
     float tmin = limit;
@@ -51,46 +54,62 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
     float shadow = 0.f;
     vec2 ring_uv = mk2(0.f, 0.f);
     float t;
+    const bool on = GATE ? active : true;
     if (COUNT && active) { if (shadow_mode) cnt.rays_s++; else cnt.rays_n++; }
 
     for (int i = 0; i < P.n_plane; i++) {
-        if (active && !shadow_mode) {
+        if (on && !shadow_mode) {
             float4 a = lds4(S.planes + i, 0), b = lds4(S.planes + i, 1);
             if (intersectPlane(ro, rd, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), tmin, t)) { tmin = t; id = make_id(RTB_TYPE_PLANE, i); }
         }
     }
-    for (int i = 0; i < P.n_sphere; i++) {
-        if (active) {
-            float4 o = lds4(S.spheres, i);
-            bool hollow = !shadow_mode && ((S.hollow[i >> 5] >> (i & 31)) & 1u);
-            if (intersectSphere(ro, rd, o, hollow, tmin, t)) {
-                if (shadow_mode) shadow = 1.f; else { tmin = t; id = make_id(RTB_TYPE_SPHERE, i); }
+    {   /* spheres, four discriminants at a time: most rays miss most spheres, so the sqrt stage is rare */
+        const bool may_hollow = !shadow_mode;                   /* inShadow passes hollow = false, rt.frag:636 */
+        int i = 0;
+        for (; i + 4 <= P.n_sphere; i += 4) {
+            float4 o0 = lds4(S.spheres, i), o1 = lds4(S.spheres, i + 1), o2 = lds4(S.spheres, i + 2), o3 = lds4(S.spheres, i + 3);
+            float b0, b1, b2, b3;
+            float h0 = sphere_disc(ro, rd, o0, b0), h1 = sphere_disc(ro, rd, o1, b1);
+            float h2 = sphere_disc(ro, rd, o2, b2), h3 = sphere_disc(ro, rd, o3, b3);
+            if (on && !(h0 < 0.f && h1 < 0.f && h2 < 0.f && h3 < 0.f)) {
+#define RTB_SPHERE_FINISH(K, O, B, H)                                                                                     \
+                if (!(H < 0.f) && sphere_finish(B, H, may_hollow && __float_as_int(O.w) < 0, tmin, t)) {                 \
+                    if (shadow_mode) shadow = 1.f; else { tmin = t; id = make_id(RTB_TYPE_SPHERE, i + K); }               \
+                }
+                RTB_SPHERE_FINISH(0, o0, b0, h0) RTB_SPHERE_FINISH(1, o1, b1, h1) RTB_SPHERE_FINISH(2, o2, b2, h2) RTB_SPHERE_FINISH(3, o3, b3, h3)
             }
         }
+        for (; i < P.n_sphere; i++) {
+            float4 o0 = lds4(S.spheres, i);
+            float b0, h0 = sphere_disc(ro, rd, o0, b0);
+            if (on) { RTB_SPHERE_FINISH(0, o0, b0, h0) }
+        }
+#undef RTB_SPHERE_FINISH
     }
     for (int i = 0; i < P.n_surf; i++) {
-        if (active) {
-            if (intersectSurface(ro, rd, S.surfs + i, tmin, t)) {
+        if (on) {
+            bool dg;
+            if (intersectSurface(ro, rd, S.surfs + i, tmin, t, dg)) {
                 if (shadow_mode) shadow = 1.f; else { tmin = t; id = make_id(RTB_TYPE_SURFACE, i); }
             }
         }
     }
     for (int i = 0; i < P.n_box; i++) {
-        if (active) {
+        if (on) {
             if (intersectBox(ro, rd, S.boxes + i, tmin, t)) {
                 if (shadow_mode) shadow = 1.f; else { tmin = t; id = make_id(RTB_TYPE_BOX, i); }
             }
         }
     }
     for (int i = 0; i < P.n_torus; i++) {
-        if (active) {
+        if (on) {
             /* intersectTorus, rt.frag:462-487 (a capped loop + straggler queue was tried here and measured SLOWER:
-             * trip counts of neighbouring lanes are correlated, lock-step loses only ~15 %) */
+             * trip counts of neighbouring lanes are correlated, lock-step loses only ~19 %) */
             TorusState st;
             if (torus_setup(ro, rd, S.tori + i, P.cull, st)) {
                 int iters;
                 t = torus_solve(st, iters);
-                if (COUNT) cnt.dk += iters;
+                if (COUNT && active) cnt.dk += iters;
                 if (t > 0 && t < 100 && t < tmin) {
                     if (shadow_mode) shadow = 1.f; else { tmin = t; id = make_id(RTB_TYPE_TORUS, i); }
                 }
@@ -99,7 +118,7 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
     }
     for (int i = 0; i < P.n_ring; i++) {
         vec2 uv = mk2(0.f, 0.f);
-        bool hit = active && intersectRing(ro, rd, S.rings + i, tmin, t, uv);
+        bool hit = on && intersectRing(ro, rd, S.rings + i, tmin, t, uv);
         int tex = S.rings[i].tex;
         if (hit && !shadow_mode) { tmin = t; id = make_id(RTB_TYPE_RING, i); ring_uv = uv; }
         if (TEX && tex > 0) {
@@ -116,12 +135,96 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
         }
     }
     for (int i = 0; i < P.n_lpoint; i++) {
-        if (active && !shadow_mode) {
+        if (on && !shadow_mode) {
             float4 o = lds4(S.lights, i);
             if (intersectSphere(ro, rd, o, false, tmin, t)) { tmin = t; id = make_id(RTB_TYPE_POINT_LIGHT, i); }
         }
     }
     tmin_out = tmin; id_out = id; shadow_out = gmin(shadow, 1.f); ring_uv_out = ring_uv;
+}
+
+/* coop_scan: the same calcInter / inShadow, for ONE ray held by the whole warp (ro, rd, mode, limit warp-uniform):
+ * lane l tests primitives l, l+32, ... of every class and the warp reduces.  Used by the persistent kernel while
+ * the frame drains (few live paths per warp): a scan that would keep 1..20 lanes busy for its full serial length
+ * takes ~1/25 of the time.  Equality with the serial scan: every accept test is `t < tmin` with the running
+ * minimum, so the serial result is the lexicographic minimum of (t, scan position) over all accepted hits, which
+ * is what the reduction computes (scan position = class rank planes<spheres<quadrics<boxes<tori<rings<lights,
+ * then index) — EXCEPT the degenerate-quadric quirk (accepts t > tmin, rt.frag:541-545), whose outcome depends
+ * on the scan order: `order_dependent` is returned true if any lane met it and the caller redoes the ray serially.
+ * Shadow mode is an any-hit with a fixed limit: OR over lanes.  No 2-D textures here (persistent kernel). */
+DEV int scan_rank(int type) {       /* rtb_prim_type -> position of the class in calcInter's order */
+    return type == RTB_TYPE_PLANE ? 0 : type == RTB_TYPE_SPHERE ? 1 : type;
+}
+template <bool COUNT>
+DEV bool coop_scan(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, bool shadow_mode, float limit,
+                   float& tmin_out, int& id_out, float& shadow_out, vec2& ring_uv_out, Counters& cnt) {
+    const int lane = threadIdx.x & 31;
+    float tmin = limit, t;
+    int id = -1;
+    bool occluded = false, order_dependent = false;
+    vec2 ring_uv = mk2(0.f, 0.f);
+    if (!shadow_mode)
+        for (int i = lane; i < P.n_plane; i += 32) {
+            float4 a = lds4(S.planes + i, 0), b = lds4(S.planes + i, 1);
+            if (intersectPlane(ro, rd, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), tmin, t)) { tmin = t; id = make_id(RTB_TYPE_PLANE, i); }
+        }
+    for (int i = lane; i < P.n_sphere; i += 32) {
+        float4 o = lds4(S.spheres, i);
+        if (intersectSphere(ro, rd, o, !shadow_mode && __float_as_int(o.w) < 0, tmin, t)) {
+            if (shadow_mode) occluded = true; else { tmin = t; id = make_id(RTB_TYPE_SPHERE, i); }
+        }
+    }
+    for (int i = lane; i < P.n_surf; i += 32) {
+        bool dg;
+        if (intersectSurface(ro, rd, S.surfs + i, tmin, t, dg)) {
+            if (shadow_mode) occluded = true; else { tmin = t; id = make_id(RTB_TYPE_SURFACE, i); }
+        }
+        order_dependent |= dg;
+    }
+    for (int i = lane; i < P.n_box; i += 32) {
+        if (intersectBox(ro, rd, S.boxes + i, tmin, t)) {
+            if (shadow_mode) occluded = true; else { tmin = t; id = make_id(RTB_TYPE_BOX, i); }
+        }
+    }
+    for (int i = lane; i < P.n_torus; i += 32) {
+        TorusState st;
+        if (torus_setup(ro, rd, S.tori + i, P.cull, st)) {
+            int iters;
+            t = torus_solve(st, iters);
+            if (COUNT) cnt.dk += iters;
+            if (t > 0 && t < 100 && t < tmin) {
+                if (shadow_mode) occluded = true; else { tmin = t; id = make_id(RTB_TYPE_TORUS, i); }
+            }
+        }
+    }
+    for (int i = lane; i < P.n_ring; i += 32) {
+        vec2 uv;
+        if (intersectRing(ro, rd, S.rings + i, tmin, t, uv)) {
+            if (shadow_mode) occluded = true; else { tmin = t; id = make_id(RTB_TYPE_RING, i); ring_uv = uv; }
+        }
+    }
+    if (!shadow_mode)
+        for (int i = lane; i < P.n_lpoint; i += 32) {
+            float4 o = lds4(S.lights, i);
+            if (intersectSphere(ro, rd, o, false, tmin, t)) { tmin = t; id = make_id(RTB_TYPE_POINT_LIGHT, i); }
+        }
+    /* warp reduction: lexicographic minimum of (t, scan position) */
+    int key = id < 0 ? 0x7fffffff : (scan_rank(id_type(id)) << 24) | id_num(id);
+    float bt = tmin; int bk = key;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ot = __shfl_xor_sync(FULL, bt, o);
+        int ok = __shfl_xor_sync(FULL, bk, o);
+        if (ok != 0x7fffffff && (bk == 0x7fffffff || ot < bt || (ot == bt && ok < bk))) { bt = ot; bk = ok; }
+    }
+    const unsigned win = __ballot_sync(FULL, bk != 0x7fffffff && key == bk);
+    const int src = win ? __ffs(win) - 1 : 0;
+    id_out = __shfl_sync(FULL, id, src);
+    if (!win) id_out = -1;
+    tmin_out = win ? bt : limit;
+    ring_uv_out = mk2(__shfl_sync(FULL, ring_uv.x, src), __shfl_sync(FULL, ring_uv.y, src));
+    shadow_out = __any_sync(FULL, occluded) ? 1.f : 0.f;
+    return __any_sync(FULL, order_dependent);
 }
 
 /* get_hit_info, rt.frag:744-784.  With TEX it must be called from warp-uniform control

@@ -139,7 +139,6 @@ PackedLayout make_layout(const rtb_defines& d) {
     uint32_t o = 0;
     L.off_plane = o;  o += align16(d.plane_size * sizeof(PPlane));
     L.off_sphere = o; o += align16(d.sphere_size * sizeof(PSphere));
-    L.off_hollow = o; o += align16(((d.sphere_size + 31) / 32) * 4);
     L.off_surf = o;   o += align16(d.surface_size * sizeof(PSurf));
     L.off_box = o;    o += align16(d.box_size * sizeof(PBox));
     L.off_torus = o;  o += align16(d.torus_size * sizeof(PTorus));
@@ -216,7 +215,7 @@ int do_render(rtb_ctx* ctx, float* target, cudaStream_t st, bool counted, bool t
         return fail(ctx, RTB_ERR_STATE, "the persistent kernel cannot render scenes that reference 2-D textures (textureNum != 0)");
     const int launch_kernel = kernel == RTB_KERNEL_QUAD ? RTB_LAUNCH_QUAD : RTB_LAUNCH_PERSISTENT;
     const int threads = kernel == RTB_KERNEL_QUAD ? QUAD_THREADS : PERSIST_THREADS;
-    const size_t smem = P.lay.total_bytes;
+    const size_t smem = kernel == RTB_KERNEL_QUAD ? (size_t)P.lay.total_bytes : PERSIST_SMEM_BYTES(P.lay.total_bytes);
     if (smem > 227 * 1024) return fail(ctx, RTB_ERR_INVALID, "packed scene (%zu bytes) exceeds the 227 KB shared-memory budget", smem);
 
     int per_sm = 0;

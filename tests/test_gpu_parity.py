@@ -5,7 +5,7 @@ Tolerance (BASELINE.json north_star): per-channel |CUDA - reference| <= 1e-4 on 
     only libm's pow/exp/atan/asin/log2 differ by an ulp).
   * fast build (FMA contraction etc.): ulp-level differences are amplified by every reflection off a curved
     surface (chaotic paths), so the bound holds for all but a stated fraction of pixels at full bounce depth,
-    and for >= 97 % of pixels when paths are cut after the first hit (silhouette / shadow-edge / solver-trip flips).
+    and for >= 95 % of pixels when paths are cut after the first hit (silhouette / shadow-edge / solver-trip flips).
 """
 import os
 
@@ -106,7 +106,7 @@ def test_fast_build_error_budget(case, procedural):
     want1 = Oracle(sc, procedural).render()
     got1, _ = gpu_render(sc, procedural, strict=0)
     frac1 = float((pixel_err(got1, want1) > TOL).mean())
-    assert frac1 <= 0.03, f"{case}: {frac1:.3%} of first-hit pixels beyond {TOL}"
+    assert frac1 <= 0.05, f"{case}: {frac1:.3%} of first-hit pixels beyond {TOL}"
 
 
 def test_quad_and_persistent_kernels_are_bit_identical(procedural):

@@ -24,9 +24,18 @@ for name, builds in (("mixed1024_4k", ("strict", "fast")), ("tori1080", ("strict
     for b in builds:
         gl.set_option("strict", 1 if b == "strict" else 0)
         ms = []
-        for _ in range(3):
+        for _ in range(6):
             gl.draw(); gl.sync(); ms.append(round(gl.stats().kernel_ms, 2))
         st = gl.stats()
         res[f"{name}_{b}"] = {"ms": ms, "grid": st.grid}
     gl.stop()
+# one rank's share of an 8-way split of the 4K frame (what strong scaling at N=8 times)
+sc = scenes.build_config("mixed1024_4k")
+gl = rtb200.GLWrapper(3840, 2160); gl.init_window(); gl.set_partition(3, 8, 16); rtb200.setup_scene(gl, sc, textures.TextureSet(cube=ts.cube))
+gl.set_option("strict", 1)
+ms = []
+for _ in range(5):
+    gl.draw(); gl.sync(); ms.append(round(gl.stats().kernel_ms, 2))
+res["mixed1024_4k_strict_rank3of8"] = ms
+gl.stop()
 print(json.dumps(res), flush=True)
