@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = "mixed1024_4k"
 METRIC = "Mrays/s"
-BLOCK_ROWS = 16
+BLOCK_ROWS = 4            # scanlines per partition block (= the kernel's tile height): finest interleave, best balance across ranks
 
 
 def parse():
@@ -238,6 +238,12 @@ def run_ours(args):
     # ---- kernel alone (roofline) on this rank ----
     ms_kernel = timed_loop(lambda: gl.draw_to(local.data_ptr(), stream.cuda_stream), max(3, args.steps), 1)
     kstats = gl.stats()
+    rank_ms = torch.tensor([ms_kernel], dtype=torch.float64, device=dev)
+    if world > 1:
+        allms = [torch.zeros_like(rank_ms) for _ in range(world)]
+        dist.all_gather(allms, rank_ms)
+        rank_ms = torch.cat(allms)
+    rank_kernel_ms = [round(float(x), 3) for x in rank_ms.tolist()]
 
     # ---- e2e: host buffers in, host frame out, wall clock ----
     def e2e_step():
@@ -299,7 +305,7 @@ def run_ours(args):
                        "parallelism": f"rowblock{BLOCK_ROWS}x{world}+gather" if world > 1 else "single",
                        "l2": "flushed between steps (256 MiB write); the 133 MB frame exceeds L2", "kernel": int(kstats.kernel_used),
                        "grid": int(kstats.grid), "block": int(kstats.block), "smem_bytes": int(kstats.smem_bytes)},
-            "rays_per_frame": rays, "pixels": pixels, "dk_iterations": dk_iters, "frame_checksum": checksum,
+            "rays_per_frame": rays, "pixels": pixels, "rank_kernel_ms": rank_kernel_ms, "dk_iterations": dk_iters, "frame_checksum": checksum,
             "e2e": {"value": e2e_value, "unit": METRIC, "ms_per_step": float(e2e_ms.item()), "h2d_bytes_per_step": int(h2d_bytes) * world,
                     "d2h_bytes_per_step": int(h * w * 16)},
             "gpu_launches": int(args.steps * world),

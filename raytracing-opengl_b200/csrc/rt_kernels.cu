@@ -45,6 +45,8 @@ DEV void stage_scene_tma(uint8_t* smem, uint64_t* mbar, const uint8_t* gsrc, uin
     }
 }
 
+DEV unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
 DEV void flush_counters(const FrameParams& P, const Counters& c) {
     if (!P.counters) return;
     auto red = [&](unsigned v, int slot) {

@@ -63,6 +63,7 @@ struct FrameParams {
     /* options */
     int32_t cull;
     unsigned long long* counters;     /* NULL unless the counting variant runs; layout = enum CounterSlot */
+    unsigned long long* cta_times;    /* NULL, or 3 globaltimer stamps per CTA: start, drain start, end (RTB_DEBUG_TIMES) */
 };
 
 enum CounterSlot {

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
     __shared__ volatile int drain_flag;
     __shared__ int n_jobs[2], next_job[2];
     if (threadIdx.x == 0) { drain_flag = 0; n_jobs[0] = n_jobs[1] = 0; next_job[0] = next_job[1] = 0; }
+    if (P.cta_times && threadIdx.x == 0) P.cta_times[blockIdx.x * 5] = globaltimer_ns();
     stage_scene_tma(smem, &mbar, P.packed, P.lay.total_bytes);          /* contains the __syncthreads that publishes the zeros above */
     const SceneView S = make_view(smem, P.lay);
     DrainJob* const jobs = (DrainJob*)(smem + ((P.lay.total_bytes + 127u) & ~127u));
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
     bool cont = false;
     bool exhausted = false;
     int parity = 0;
+    unsigned dbg_jobs = 0, dbg_trips = 0;
 
     for (;;) {
         /* ---- refill idle lanes with fresh pixels ---- */
@@ -94,7 +96,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
                     }
                 }
             }
-            if (base + (unsigned)__popc(want) >= total) { exhausted = true; drain_flag = 1; }   /* warp-uniform: the counter passed the last pixel */
+            if (base + (unsigned)__popc(want) >= total) {       /* warp-uniform: the counter passed the last pixel */
+                if (P.cta_times && lane == 0 && !drain_flag) P.cta_times[blockIdx.x * 5 + 1] = globaltimer_ns();
+                exhausted = true; drain_flag = 1;
+            }
         }
         if (drain_flag) exhausted = true;                       /* some warp of this CTA saw the end of the frame: no more refills */
         const bool active = px >= 0;
@@ -117,6 +122,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
             __syncthreads();
             const int n = n_jobs[parity];
             if (n == 0) break;                                  /* CTA-uniform: every path of this CTA has ended */
+            dbg_jobs += n; dbg_trips++;
             if (threadIdx.x == 0) { n_jobs[parity ^ 1] = 0; next_job[parity ^ 1] = 0; }   /* nobody touches the other set before the next barrier */
             for (;;) {
                 int j = 0;
@@ -126,14 +132,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
                 const DrainJob J = jobs[j];                     /* broadcast loads */
                 const vec3 bro = mk3(J.ro[0], J.ro[1], J.ro[2]), brd = mk3(J.rd[0], J.rd[1], J.rd[2]);
                 float r_tm, r_sh; int r_id; vec2 r_uv;
-                const unsigned dk_before = cnt.dk;
-                if (coop_scan<COUNT>(P, S, bro, brd, J.shadow != 0, J.limit, r_tm, r_id, r_sh, r_uv, cnt)) {
-                    /* a degenerate quadric makes the result depend on the scan order: redo this ray the serial way, on lane 0 */
-                    cnt.dk = dk_before;
-                    Counters scratch = {};
-                    scan_scene<COUNT, false, true>(P, S, bro, brd, lane == 0, J.shadow != 0, J.limit, 0, r_tm, r_id, r_sh, r_uv, scratch);
-                    if (COUNT) cnt.dk += scratch.dk;
-                }
+                coop_scan<COUNT>(P, S, bro, brd, J.shadow != 0, J.limit, r_tm, r_id, r_sh, r_uv, cnt);
                 if (lane == 0) { DrainResult r = { r_tm, r_id, r_sh, r_uv.x, r_uv.y, { 0, 0, 0 } }; results[j] = r; }
             }
             __syncthreads();
@@ -269,6 +268,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
             px = -1;
         }
     }
+    if (P.cta_times && threadIdx.x == 0) { P.cta_times[blockIdx.x * 5 + 2] = globaltimer_ns(); P.cta_times[blockIdx.x * 5 + 3] = ((unsigned long long)dbg_trips << 32) | dbg_jobs; }
     if (COUNT) flush_counters(P, cnt);
 }
 

@@ -88,8 +88,7 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
     }
     for (int i = 0; i < P.n_surf; i++) {
         if (on) {
-            bool dg;
-            if (intersectSurface(ro, rd, S.surfs + i, tmin, t, dg)) {
+            if (intersectSurface(ro, rd, S.surfs + i, tmin, t)) {
                 if (shadow_mode) shadow = 1.f; else { tmin = t; id = make_id(RTB_TYPE_SURFACE, i); }
             }
         }
@@ -145,23 +144,35 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
 
 /* coop_scan: the same calcInter / inShadow, for ONE ray held by the whole warp (ro, rd, mode, limit warp-uniform):
  * lane l tests primitives l, l+32, ... of every class and the warp reduces.  Used by the persistent kernel while
- * the frame drains (few live paths per warp): a scan that would keep 1..20 lanes busy for its full serial length
- * takes ~1/25 of the time.  Equality with the serial scan: every accept test is `t < tmin` with the running
- * minimum, so the serial result is the lexicographic minimum of (t, scan position) over all accepted hits, which
- * is what the reduction computes (scan position = class rank planes<spheres<quadrics<boxes<tori<rings<lights,
- * then index) — EXCEPT the degenerate-quadric quirk (accepts t > tmin, rt.frag:541-545), whose outcome depends
- * on the scan order: `order_dependent` is returned true if any lane met it and the caller redoes the ray serially.
- * Shadow mode is an any-hit with a fixed limit: OR over lanes.  No 2-D textures here (persistent kernel). */
+ * the frame drains (rt_persistent.cuh).  Equality with the serial scan: every accept test but one is `t < tmin`
+ * with the running minimum, so the serial result is the lexicographic minimum of (t, scan position) over all
+ * candidates, which is what the reductions compute (scan position = class rank planes < spheres < quadrics <
+ * boxes < tori < rings < lights, then index).  The exception is the degenerate-quadric quirk (accepts t > tmin,
+ * rt.frag:541-545): quadrics are therefore resolved between two reductions, 32 at a time, and a round that
+ * contains a degenerate candidate is replayed in index order against the running minimum (warp shuffles).
+ * Shadow mode is an any-hit against the fixed limit: OR over lanes.  No 2-D textures here (persistent kernel). */
 DEV int scan_rank(int type) {       /* rtb_prim_type -> position of the class in calcInter's order */
     return type == RTB_TYPE_PLANE ? 0 : type == RTB_TYPE_SPHERE ? 1 : type;
 }
+DEV int scan_key(int id) { return id < 0 ? 0x7fffffff : (scan_rank(id_type(id)) << 24) | id_num(id); }
+/* lexicographic minimum of (t, key) over the warp; every lane gets the winner's (t, id) */
+DEV void warp_nearest(float& t, int& id) {
+    float bt = t; int bk = scan_key(id), bid = id;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ot = __shfl_xor_sync(FULL, bt, o);
+        int ok = __shfl_xor_sync(FULL, bk, o), oid = __shfl_xor_sync(FULL, bid, o);
+        if (ok != 0x7fffffff && (bk == 0x7fffffff || ot < bt || (ot == bt && ok < bk))) { bt = ot; bk = ok; bid = oid; }
+    }
+    t = bt; id = bid;
+}
 template <bool COUNT>
-DEV bool coop_scan(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, bool shadow_mode, float limit,
+DEV void coop_scan(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, bool shadow_mode, float limit,
                    float& tmin_out, int& id_out, float& shadow_out, vec2& ring_uv_out, Counters& cnt) {
     const int lane = threadIdx.x & 31;
     float tmin = limit, t;
     int id = -1;
-    bool occluded = false, order_dependent = false;
+    bool occluded = false;
     vec2 ring_uv = mk2(0.f, 0.f);
     if (!shadow_mode)
         for (int i = lane; i < P.n_plane; i += 32) {
@@ -174,12 +185,29 @@ DEV bool coop_scan(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, b
             if (shadow_mode) occluded = true; else { tmin = t; id = make_id(RTB_TYPE_SPHERE, i); }
         }
     }
-    for (int i = lane; i < P.n_surf; i += 32) {
-        bool dg;
-        if (intersectSurface(ro, rd, S.surfs + i, tmin, t, dg)) {
-            if (shadow_mode) occluded = true; else { tmin = t; id = make_id(RTB_TYPE_SURFACE, i); }
+    if (shadow_mode) {
+        for (int i = lane; i < P.n_surf; i += 32)
+            if (intersectSurface(ro, rd, S.surfs + i, tmin, t)) occluded = true;
+    } else if (P.n_surf > 0) {
+        warp_nearest(tmin, id);                                 /* the running minimum after planes and spheres, on every lane */
+        for (int base = 0; base < P.n_surf; base += 32) {
+            const int i = base + lane;
+            int kind = 0;
+            t = 0.f;
+            if (i < P.n_surf) kind = surface_candidate(ro, rd, S.surfs + i, t);
+            if (!__any_sync(FULL, kind == 2)) {
+                float ct = surface_accept(kind, t, tmin) ? t : tmin;
+                int cid = surface_accept(kind, t, tmin) ? make_id(RTB_TYPE_SURFACE, i) : id;
+                warp_nearest(ct, cid);
+                tmin = ct; id = cid;
+            } else {
+                for (int l = 0; l < 32; l++) {                  /* replay the round in index order */
+                    const int k = __shfl_sync(FULL, kind, l);
+                    const float tt = __shfl_sync(FULL, t, l);
+                    if (surface_accept(k, tt, tmin)) { tmin = tt; id = make_id(RTB_TYPE_SURFACE, base + l); }
+                }
+            }
         }
-        order_dependent |= dg;
     }
     for (int i = lane; i < P.n_box; i += 32) {
         if (intersectBox(ro, rd, S.boxes + i, tmin, t)) {
@@ -208,23 +236,15 @@ DEV bool coop_scan(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, b
             float4 o = lds4(S.lights, i);
             if (intersectSphere(ro, rd, o, false, tmin, t)) { tmin = t; id = make_id(RTB_TYPE_POINT_LIGHT, i); }
         }
-    /* warp reduction: lexicographic minimum of (t, scan position) */
-    int key = id < 0 ? 0x7fffffff : (scan_rank(id_type(id)) << 24) | id_num(id);
-    float bt = tmin; int bk = key;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        float ot = __shfl_xor_sync(FULL, bt, o);
-        int ok = __shfl_xor_sync(FULL, bk, o);
-        if (ok != 0x7fffffff && (bk == 0x7fffffff || ot < bt || (ot == bt && ok < bk))) { bt = ot; bk = ok; }
-    }
-    const unsigned win = __ballot_sync(FULL, bk != 0x7fffffff && key == bk);
+    const int my_id = id;
+    warp_nearest(tmin, id);
+    /* the winner's ring uv: the lowest lane that holds the winning id (a ring id is held by exactly one lane) */
+    const unsigned win = __ballot_sync(FULL, id >= 0 && my_id == id);
     const int src = win ? __ffs(win) - 1 : 0;
-    id_out = __shfl_sync(FULL, id, src);
-    if (!win) id_out = -1;
-    tmin_out = win ? bt : limit;
     ring_uv_out = mk2(__shfl_sync(FULL, ring_uv.x, src), __shfl_sync(FULL, ring_uv.y, src));
+    id_out = id;
+    tmin_out = id >= 0 ? tmin : limit;
     shadow_out = __any_sync(FULL, occluded) ? 1.f : 0.f;
-    return __any_sync(FULL, order_dependent);
 }
 
 /* get_hit_info, rt.frag:744-784.  With TEX it must be called from warp-uniform control

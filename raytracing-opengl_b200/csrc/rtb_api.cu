@@ -12,6 +12,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "../../include/rtb200.h"
 #include "rt_launch.h"
@@ -39,6 +40,8 @@ struct rtb_ctx {
     bool dirty = true;
     unsigned int* tile_counter = nullptr;
     unsigned long long* counters = nullptr;
+    unsigned long long* cta_times = nullptr;     /* RTB_DEBUG_TIMES=1: per-CTA start / drain / end stamps, printed by rtb_sync */
+    int cta_times_n = 0;
     float* fb = nullptr; size_t fb_floats = 0;
     uint8_t* cube = nullptr; int cube_w = 0, cube_h = 0;
     Tex2D tex[6];
@@ -206,6 +209,7 @@ int do_render(rtb_ctx* ctx, float* target, cudaStream_t st, bool counted, bool t
     P.n_tiles_x = (ctx->width + 7) / 8; P.n_tiles_y = (ctx->local_rows + 3) / 4;
     P.cull = ctx->opt_cull;
     P.counters = counted ? ctx->counters : nullptr;
+    P.cta_times = nullptr;
 
     const bool strict = ctx->opt_strict != 0;
     int kernel = ctx->opt_kernel;
@@ -224,6 +228,12 @@ int do_render(rtb_ctx* ctx, float* target, cudaStream_t st, bool counted, bool t
     if (ctx->opt_ctas_per_sm > 0 && ctx->opt_ctas_per_sm < per_sm) per_sm = ctx->opt_ctas_per_sm;
     const int grid = ctx->n_sm * per_sm;                 /* persistent: a whole number of CTAs on every one of the SMs */
 
+    if (getenv("RTB_DEBUG_TIMES") && kernel == RTB_KERNEL_PERSISTENT) {
+        if (!ctx->cta_times) CU(cudaMalloc(&ctx->cta_times, (size_t)grid * 5 * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(ctx->cta_times, 0, (size_t)grid * 5 * sizeof(unsigned long long), st));
+        ctx->cta_times_n = grid;
+        P.cta_times = ctx->cta_times;
+    }
     if (st != ctx->stream) {                             /* uploads ran on the context stream: order them before this frame */
         CU(cudaEventRecord(ctx->ev_upload, ctx->stream));
         CU(cudaStreamWaitEvent(st, ctx->ev_upload, 0));
@@ -287,6 +297,7 @@ void rtb_destroy(rtb_ctx* ctx) {
     if (ctx->packed) cudaFree(ctx->packed);
     if (ctx->tile_counter) cudaFree(ctx->tile_counter);
     if (ctx->counters) cudaFree(ctx->counters);
+    if (ctx->cta_times) cudaFree(ctx->cta_times);
     if (ctx->fb) cudaFree(ctx->fb);
     if (ctx->cube) cudaFree(ctx->cube);
     for (int u = 0; u < 6; u++) if (ctx->tex[u].dev) cudaFree(ctx->tex[u].dev);
@@ -405,6 +416,37 @@ int rtb_sync(rtb_ctx* ctx) {
     if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "null context");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->cta_times && ctx->cta_times_n) {
+        std::vector<unsigned long long> t((size_t)ctx->cta_times_n * 5);
+        if (cudaMemcpy(t.data(), ctx->cta_times, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            unsigned long long t0 = ~0ull, dmin = ~0ull, dmax = 0, emin = ~0ull, emax = 0;
+            for (int i = 0; i < ctx->cta_times_n; i++) if (t[i * 5] && t[i * 5] < t0) t0 = t[i * 5];
+            std::vector<double> ends;
+            for (int i = 0; i < ctx->cta_times_n; i++) {
+                unsigned long long d = t[i * 5 + 1], e = t[i * 5 + 2];
+                if (d) { if (d < dmin) dmin = d; if (d > dmax) dmax = d; }
+                if (e) { if (e < emin) emin = e; if (e > emax) emax = e; ends.push_back((double)(e - t0) * 1e-6); }
+            }
+            std::sort(ends.begin(), ends.end());
+            fprintf(stderr, "cta times (ms from first CTA start): drain start %.2f..%.2f, CTA end min %.2f p25 %.2f median %.2f p75 %.2f p95 %.2f max %.2f\n",
+                    (double)(dmin - t0) * 1e-6, (double)(dmax - t0) * 1e-6, ends.empty() ? 0. : ends.front(), ends.empty() ? 0. : ends[ends.size() / 4],
+                    ends.empty() ? 0. : ends[ends.size() / 2], ends.empty() ? 0. : ends[ends.size() * 3 / 4], ends.empty() ? 0. : ends[ends.size() * 95 / 100], ends.empty() ? 0. : ends.back());
+            /* the five slowest CTAs: end time, drain trips, drain jobs, serial fallbacks */
+            std::vector<int> order(ctx->cta_times_n);
+            for (int i = 0; i < ctx->cta_times_n; i++) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](int a, int b) { return t[a * 5 + 2] > t[b * 5 + 2]; });
+            unsigned long long tj = 0, tf = 0;
+            for (int i = 0; i < ctx->cta_times_n; i++) { tj += t[i * 5 + 3] & 0xffffffffu; tf += t[i * 5 + 4]; }
+            fprintf(stderr, "  drain jobs total %llu (mean %.0f per CTA), fallbacks %llu; slowest:", tj, (double)tj / ctx->cta_times_n, tf);
+            for (int k = 0; k < 5 && k < ctx->cta_times_n; k++) {
+                int i = order[k];
+                fprintf(stderr, " [end %.2f trips %llu jobs %llu fb %llu]", (double)(t[i * 5 + 2] - t0) * 1e-6, t[i * 5 + 3] >> 32, t[i * 5 + 3] & 0xffffffffu, t[i * 5 + 4]);
+            }
+            int i = order[ctx->cta_times_n / 2];
+            fprintf(stderr, " median [end %.2f trips %llu jobs %llu fb %llu]\n", (double)(t[i * 5 + 2] - t0) * 1e-6, t[i * 5 + 3] >> 32, t[i * 5 + 3] & 0xffffffffu, t[i * 5 + 4]);
+        }
+        ctx->cta_times_n = 0;
+    }
     if (ctx->timed_pending) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.kernel_ms = ms;

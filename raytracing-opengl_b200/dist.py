@@ -25,6 +25,16 @@ def local_row_map(height: int, rank: int, world: int, block_rows: int = BLOCK_RO
     return torch.tensor(rows, dtype=torch.long)
 
 
+_ROW_MAPS = {}
+
+
+def _device_row_map(height, rank, world, block_rows, device):
+    key = (height, rank, world, block_rows, str(device))
+    if key not in _ROW_MAPS:
+        _ROW_MAPS[key] = local_row_map(height, rank, world, block_rows).to(device)
+    return _ROW_MAPS[key]
+
+
 def max_local_rows(height: int, world: int, block_rows: int = BLOCK_ROWS) -> int:
     return max(len(local_row_map(height, r, world, block_rows)) for r in range(world))
 
@@ -59,7 +69,7 @@ def gather_frame(local: torch.Tensor, height: int, rank: int, world: int, block_
         if out is None:
             out = torch.empty((height,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         for r in range(world):
-            rows = local_row_map(height, r, world, block_rows).to(local.device)
+            rows = _device_row_map(height, r, world, block_rows, local.device)      # cached: no per-frame host work
             out.index_copy_(0, rows, scratch[r][: len(rows)])
         return out
     dist.gather(local, gather_list=None, dst=0)
