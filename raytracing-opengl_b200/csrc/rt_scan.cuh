@@ -11,6 +11,9 @@
  */
 #pragma once
 #include "rt_device.cuh"
+#ifndef RTB_SCALAR_DK
+#define RTB_SCALAR_DK 0
+#endif
 
 namespace RTB_NS {
 
@@ -100,6 +103,7 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
             }
         }
     }
+    const PackK K = make_packk(P);
     for (int i = 0; i < P.n_torus; i++) {
         if (on) {
             /* intersectTorus, rt.frag:462-487 (a capped loop + straggler queue was tried here and measured SLOWER:
@@ -107,7 +111,7 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
             TorusState st;
             if (torus_setup(ro, rd, S.tori + i, P.cull, st)) {
                 int iters;
-                t = torus_solve(st, iters);
+                t = RTB_SCALAR_DK ? torus_solve_scalar(st, iters) : torus_solve(K, st, iters);
                 if (COUNT && active) cnt.dk += iters;
                 if (t > 0 && t < 100 && t < tmin) {
                     if (shadow_mode) shadow = 1.f; else { tmin = t; id = make_id(RTB_TYPE_TORUS, i); }
@@ -214,11 +218,12 @@ DEV void coop_scan(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, b
             if (shadow_mode) occluded = true; else { tmin = t; id = make_id(RTB_TYPE_BOX, i); }
         }
     }
+    const PackK K = make_packk(P);
     for (int i = lane; i < P.n_torus; i += 32) {
         TorusState st;
         if (torus_setup(ro, rd, S.tori + i, P.cull, st)) {
             int iters;
-            t = torus_solve(st, iters);
+            t = RTB_SCALAR_DK ? torus_solve_scalar(st, iters) : torus_solve(K, st, iters);
             if (COUNT) cnt.dk += iters;
             if (t > 0 && t < 100 && t < tmin) {
                 if (shadow_mode) occluded = true; else { tmin = t; id = make_id(RTB_TYPE_TORUS, i); }

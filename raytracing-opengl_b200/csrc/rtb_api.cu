@@ -208,6 +208,7 @@ int do_render(rtb_ctx* ctx, float* target, cudaStream_t st, bool counted, bool t
     P.tile_counter = ctx->tile_counter;
     P.n_tiles_x = (ctx->width + 7) / 8; P.n_tiles_y = (ctx->local_rows + 3) / 4;
     P.cull = ctx->opt_cull;
+    P.k_one = 1.0f; P.k_neg_zero = -0.0f; P.k_neg_one = -1.0f;
     P.counters = counted ? ctx->counters : nullptr;
     P.cta_times = nullptr;
 
