@@ -215,10 +215,12 @@ def run_ours(args):
             fn()
             b.record(stream)
         barrier()
-        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+        local_ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+        ms = torch.tensor([local_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / steps
+        timed_loop.local_ms = local_ms
+        return float(ms.item())
 
     # ---- exact work count (instrumented variant, untimed) ----
     st = gl.draw_counted()
@@ -238,7 +240,7 @@ def run_ours(args):
     # ---- kernel alone (roofline) on this rank ----
     ms_kernel = timed_loop(lambda: gl.draw_to(local.data_ptr(), stream.cuda_stream), max(3, args.steps), 1)
     kstats = gl.stats()
-    rank_ms = torch.tensor([ms_kernel], dtype=torch.float64, device=dev)
+    rank_ms = torch.tensor([timed_loop.local_ms], dtype=torch.float64, device=dev)
     if world > 1:
         allms = [torch.zeros_like(rank_ms) for _ in range(world)]
         dist.all_gather(allms, rank_ms)
@@ -291,10 +293,11 @@ def run_ours(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         base, _, _ = cpu_rate(scene, args.cpu_seconds)
-        traffic = None
+        traffic, ncu_note = None, None
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = prof.get(f"{args.workload}_{args.build}")
+            prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}_{args.build}", {})
+            traffic = prof.get("dram_bytes_per_launch")
+            ncu_note = {k: v for k, v in prof.items() if k != "dram_bytes_per_launch"}
         except Exception:
             pass
         line = {
@@ -311,12 +314,14 @@ def run_ours(args):
             "gpu_launches": int(args.steps * world),
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": traffic, "kernel": "persistent_kernel" if kstats.kernel_used == 2 else "quad_kernel",
+                         "traffic": traffic, "ncu": ncu_note, "kernel": "persistent_kernel" if kstats.kernel_used == 2 else "quad_kernel",
                          "kernel_ms": ms_kernel, "algorithmic_flops_per_launch": local_flops,
                          "peak_source": "FFMA microbenchmark measured in this run (rtb_measure_fp32_peak); MEASURED_PEAKS.json has no fp32 entry; "
                                         "nominal 74.4 = 148 SM x 128 lanes x 2 x 1.965 GHz",
-                         "note": "fp32 CUDA-core bound (no dense contraction, north_star); strict build issues FMUL+FADD where the fast build "
-                                 "issues FFMA, so 0.5 is its ceiling against an FFMA peak",
+                         "frac_of_unfused_peak": achieved / (peak / 2) if peak else None,
+                         "note": "fp32 CUDA-core bound (no dense contraction, north_star). The strict build rounds every multiply and add "
+                                 "separately (bit-parity with the shader), i.e. one flop per FMA-pipe lane-cycle where the FFMA peak counts two: "
+                                 "0.5 is its ceiling against `peak`; frac_of_unfused_peak is the fraction of that ceiling",
                          "hbm": {"achieved_GBs": alg_bytes / (ms_kernel * 1e-3) / 1e9, "peak_GBs": hbm_peak,
                                  "frac": alg_bytes / (ms_kernel * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": alg_bytes}},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},

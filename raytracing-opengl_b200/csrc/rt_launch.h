@@ -6,9 +6,11 @@
 #include "rt_params.h"
 
 #define QUAD_THREADS 128
-/* persistent kernel: ONE 16-warp CTA per SM (all warps share one staged scene and, while the frame drains, one job pool) */
+/* persistent kernel: ONE 20-warp CTA per SM (all warps share one staged scene and, while the frame drains, one job pool).
+ * 640 threads cap ptxas at 96 registers (a 250-byte spill outside the hot loops); measured against 512 threads / 124
+ * registers: mixed1024@4K 441 -> 437 ms, spheres4k 35.2 -> 33.5 ms; 768 threads / 80 registers is slower (445 ms). */
 #ifndef PERSIST_THREADS
-#define PERSIST_THREADS 512
+#define PERSIST_THREADS 640
 #endif
 #ifndef PERSIST_MIN_BLOCKS
 #define PERSIST_MIN_BLOCKS 1
