@@ -36,7 +36,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persistent_kernel(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ volatile int drain_flag;
+    __shared__ int drain_flag;                                  /* 0 -> 1 once; read and written with atomics only */
     __shared__ int n_jobs[2], next_job[2];
     if (threadIdx.x == 0) { drain_flag = 0; n_jobs[0] = n_jobs[1] = 0; next_job[0] = next_job[1] = 0; }
     if (P.cta_times && threadIdx.x == 0) P.cta_times[blockIdx.x * 5] = globaltimer_ns();
@@ -97,11 +97,15 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
                 }
             }
             if (base + (unsigned)__popc(want) >= total) {       /* warp-uniform: the counter passed the last pixel */
-                if (P.cta_times && lane == 0 && !drain_flag) P.cta_times[blockIdx.x * 5 + 1] = globaltimer_ns();
-                exhausted = true; drain_flag = 1;
+                exhausted = true;
+                if (lane == 0 && atomicExch(&drain_flag, 1) == 0 && P.cta_times) P.cta_times[blockIdx.x * 5 + 1] = globaltimer_ns();
             }
         }
-        if (drain_flag) exhausted = true;                       /* some warp of this CTA saw the end of the frame: no more refills */
+        if (!exhausted) {                                       /* did some other warp of this CTA see the end of the frame?  then no more refills */
+            int f = 0;
+            if (lane == 0) f = atomicAdd(&drain_flag, 0);
+            exhausted = __shfl_sync(FULL, f, 0) != 0;
+        }
         const bool active = px >= 0;
         float tm, shadow; int id; vec2 ruv;
 

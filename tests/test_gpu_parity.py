@@ -273,3 +273,29 @@ def test_full_size_8k_partition_invariance(procedural):
     full, _ = gpu_render(sc, procedural)
     tiled = _render_partitioned(sc, procedural, 8)
     assert np.array_equal(full.view(np.uint32), tiled.view(np.uint32))
+
+
+def test_partition_with_empty_ranks_and_tiny_canvases(procedural):
+    """More ranks than 4-scanline blocks (some contexts own no pixels at all) and canvases far smaller than the machine
+    (every CTA of the persistent kernel goes straight to its cooperative drain): frames stay bit-identical."""
+    for (w, h) in ((30, 10), (64, 48)):
+        sc = scenes.synthetic_scene("mini4", w, h, 5)
+        want = Oracle(sc, procedural).render()
+        full, _ = gpu_render(sc, procedural, kernel=KERNEL_PERSISTENT)
+        assert pixel_err(full, want).max() <= TOL
+        world, parts = 8, []
+        for r in range(world):
+            gl = rtb200.GLWrapper(w, h)
+            gl.init_window()
+            try:
+                gl.set_partition(r, world, 4)
+                rtb200.setup_scene(gl, sc, procedural)
+                gl.set_option("kernel", KERNEL_PERSISTENT)
+                gl.set_option("strict", 1)
+                gl.draw()
+                parts.append(gl.read_pixels())
+            finally:
+                gl.stop()
+        assert sum(p.shape[0] for p in parts) == h
+        assert any(p.shape[0] == 0 for p in parts) == ((h + 3) // 4 < world)
+        assert np.array_equal(rtb200.gather_rows(parts, h, world, 4), full)

@@ -93,3 +93,36 @@ def test_unchanged_main_cpp_renders_the_default_scene_like_the_oracle():
             np.savez_compressed(os.path.join(out, "default_scene_t0.npz"), width=256, height=256,
                                 **{a: np.frombuffer(sc.array(a).tobytes(), dtype=np.uint8) for a in
                                    ("spheres", "surfaces", "boxes", "toruses", "rings", "lights_point", "lights_direct")})
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isfile(BIN), reason="rt_headless did not travel (built only where /root/reference exists)")
+def test_unchanged_frame_loop_animates_and_reuploads_every_frame():
+    """SURVEY.md 8f-2, the per-frame update path: main.cpp's loop (update_scene :197-246 -> SceneManager::update ->
+    update_buffers :266-276 -> draw) runs three frames on the deterministic clock; the LAST frame must match the oracle
+    fed with the uniform-buffer bytes of the last upload, and must differ from the first (the scene moved)."""
+    import rtb200  # noqa: F401
+    from oracle.binding import Oracle
+    from rtb200 import scene as S
+    from rtb200.scene import SceneContainer
+    from rtb200.textures import TextureSet
+    from util import pixel_err
+    with tempfile.TemporaryDirectory() as td:
+        env = dict(os.environ, RT_WIDTH="192", RT_HEIGHT="108", RT_ITERATIONS="3", RT_FRAMES="3", RT_DUMP_DIR=td, RT_STRICT="1")
+        r = subprocess.run([BIN], capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        frames = [np.load(os.path.join(td, f"frame_{i:04d}.npy")) for i in range(3)]
+        assert frames[2].shape == (108, 192, 4)
+        assert np.abs(frames[2] - frames[0]).max() > 1e-3            # the box and the torus spin (main.cpp:234-245)
+        sc = SceneContainer()
+        for name, attr, dt in (("spheres_buf", "spheres", S.rt_sphere), ("surfaces_buf", "surfaces", S.rt_surface), ("boxes_buf", "boxes", S.rt_box),
+                               ("toruses_buf", "toruses", S.rt_torus), ("rings_buf", "rings", S.rt_ring), ("lights_point_buf", "lights_point", S.rt_light_point),
+                               ("lights_direct_buf", "lights_direct", S.rt_light_direct)):
+            setattr(sc, attr, np.frombuffer(np.load(os.path.join(td, name + ".npy")).tobytes(), dtype=dt).copy())
+        sc.scene = np.frombuffer(np.load(os.path.join(td, "scene_buf.npy")).tobytes(), dtype=S.rt_scene)[0].copy()
+        sc.scene["reflect_depth"] = 3
+        sc.ambient_color, sc.shadow_ambient = (0.025,) * 3, (0.1,) * 3
+        ts = TextureSet(cube=[np.load(os.path.join(td, f"cube_{f}.npy")) for f in range(6)],
+                        tex2d={u: np.load(os.path.join(td, f"tex_{u}.npy")) for u in range(1, 6)})
+        err = pixel_err(frames[2], Oracle(sc, ts).render())
+        assert err.max() <= 1e-4, (float(err.max()), int((err > 1e-4).sum()))
