@@ -126,6 +126,15 @@ def cpu_rate(scene, target_seconds, steps=1, warmup=0):
             "seconds_per_step": mean}, rays, mean
 
 
+def describe(scene):
+    """Workload facts for the JSON line, from the scene itself."""
+    d = scene.get_defines()
+    counts = {k: int(d[k + "_size"]) for k in ("sphere", "plane", "surface", "box", "torus", "ring", "light_point", "light_direct")}
+    prims = sum(counts[k] for k in ("sphere", "plane", "surface", "box", "torus", "ring"))
+    text = " + ".join(f"{v} {k}" for k, v in counts.items() if v and not k.startswith("light")) + f", {counts['light_point'] + counts['light_direct']} lights"
+    return text, prims, int(d["iterations"])
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -135,10 +144,11 @@ def run_reference(args):
     scene = scenes.build_config(args.workload, args.scale)
     base, rays, mean = cpu_rate(scene, args.cpu_seconds, steps=args.steps, warmup=min(args.warmup, 1))
     w, h = int(scene.scene["canvas_width"]), int(scene.scene["canvas_height"])
+    _, n_prims, n_bounces = describe(scene)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "width": w, "height": h, "primitives": 1024, "bounces": 8,
+            "config": {"workload": args.workload, "width": w, "height": h, "primitives": n_prims, "bounces": n_bounces,
                        "note": "reference = the repo's GLSL shader executed on the host CPU cores (no GL available in this image); "
                                "each step renders a bounded seeded sample of the frame's quads"},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -178,7 +188,8 @@ def run_ours(args):
         t[: a.nbytes] = torch.from_numpy(np.frombuffer(a.tobytes(), dtype=np.uint8).copy())
         pinned[name] = t.numpy()[: a.nbytes]
     from rtb200.textures import TextureSet, procedural_textures
-    sky = TextureSet(cube=procedural_textures(cube_size=512).cube)        # the reference's asset files do not travel
+    # the reference's asset files do not travel: procedural cubemap (and 2-D textures where the scene references them)
+    sky = procedural_textures(cube_size=512) if scene.uses_textures() else TextureSet(cube=procedural_textures(cube_size=512).cube)
     handles = rtb200.setup_scene(gl, scene, sky)
     h2d_bytes = sum(v.nbytes for v in pinned.values())
     gl.set_option("strict", strict)
@@ -283,6 +294,7 @@ def run_ours(args):
         gl.set_option("cull", 0)
 
     if rank == 0:
+        scene_text, n_prims, n_bounces = describe(scene)
         peak = rtb200.measure_fp32_peak(local_rank)
         achieved = local_flops / (ms_kernel * 1e-3) / 1e12
         alg_bytes = (h * w * 16) / world + h2d_bytes
@@ -303,8 +315,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "scene": "mixed1024: 512 spheres + 256 boxes + 192 quadrics + 64 tori, 2 lights (PCG32 seed 5)",
-                       "width": w, "height": h, "primitives": 1024, "bounces": 8, "build": args.build, "skybox": "procedural 512^2 cubemap",
+            "config": {"workload": args.workload, "scene": scene_text + " (SURVEY.md 8d generator)",
+                       "width": w, "height": h, "primitives": n_prims, "bounces": n_bounces, "build": args.build, "skybox": "procedural 512^2 cubemap",
                        "parallelism": f"rowblock{BLOCK_ROWS}x{world}+gather" if world > 1 else "single",
                        "l2": "flushed between steps (256 MiB write); the 133 MB frame exceeds L2", "kernel": int(kstats.kernel_used),
                        "grid": int(kstats.grid), "block": int(kstats.block), "smem_bytes": int(kstats.smem_bytes)},
