@@ -1,6 +1,6 @@
 /* rt_persistent.cuh — persistent-threads kernel for scenes without 2-D textures.
  *
- * One CTA (or a few) per SM lives for the whole frame.  Every LANE owns one
+ * ONE 20-warp CTA per SM lives for the whole frame.  Every LANE owns one
  * pixel's path at a time and runs a small job machine whose only expensive
  * state is "scan the whole scene with this ray":
  *
@@ -8,14 +8,21 @@
  *      SUB     calcInter inside getReflectedColor              (rt.frag:792)
  *      SHADOW  inShadow for light l of the pending calcShade   (rt.frag:667)
  *
- * The warp executes ONE unified scan per loop trip in which each lane has its
- * own ray and its own mode (nearest / shadow); between scans each lane
- * post-processes its result (hit attributes, Fresnel, Phong accumulation) and
- * posts its next job.  A lane whose path ended takes a fresh pixel from the
+ * Steady state: the warp executes ONE unified scan per loop trip in which each
+ * lane has its own ray and its own mode (nearest / shadow); between scans each
+ * lane post-processes its result (hit attributes, Fresnel, Phong accumulation)
+ * and posts its next job.  A lane whose path ended takes a fresh pixel from the
  * frame's atomic counter immediately (ballot-compacted, one atomicAdd per
- * warp), so the scan — >95 % of the work — always runs with (nearly) full
- * warps no matter how differently deep neighbouring pixels bounce.  Per-pixel
- * arithmetic and its order are untouched: results equal the quad kernel's.
+ * warp), so the scan — >95 % of the work — runs with full warps no matter how
+ * differently deep neighbouring pixels bounce.
+ *
+ * Drain: once the counter has passed the last pixel, lanes fall idle one by
+ * one.  From then on all warps of the CTA pool the scans of their live paths
+ * in shared memory and serve them one ray per warp (coop_scan, rt_scan.cuh),
+ * so the SM stays busy until its last path ends.
+ *
+ * Per-pixel arithmetic and its order are untouched in both phases: results
+ * equal the quad kernel's bit for bit.
  */
 #pragma once
 #include "rt_scan.cuh"
