@@ -43,6 +43,7 @@ struct rtb_ctx {
     unsigned long long* cta_times = nullptr;     /* RTB_DEBUG_TIMES=1: per-CTA start / drain / end stamps, printed by rtb_sync */
     int cta_times_n = 0;
     float* fb = nullptr; size_t fb_floats = 0;
+    uint8_t* fb8 = nullptr;                       /* RGBA8 copy of the frame, made on demand by rtb_read_rgba8 */
     uint8_t* cube = nullptr; int cube_w = 0, cube_h = 0;
     Tex2D tex[6];
     int opt_kernel = RTB_KERNEL_AUTO, opt_strict = 0, opt_cull = 0, opt_ctas_per_sm = 0;
@@ -52,6 +53,20 @@ struct rtb_ctx {
 };
 
 namespace {
+
+/* GL unorm8 conversion of the colour buffer (the reference renders into RGBA8, GLWrapper.cpp:127,216): clamp to [0,1],
+ * scale by 255, round to nearest; NaN -> 0.  One float4 in, one uchar4 out per thread: a pure HBM stream. */
+__global__ void rgba8_kernel(const float4* __restrict__ src, uchar4* __restrict__ dst, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 v = src[i];
+    auto q = [](float x) -> unsigned char {
+        x = x < 0.f ? 0.f : (x > 1.f ? 1.f : x);
+        if (!(x == x)) x = 0.f;
+        return (unsigned char)__fadd_rn(__fmul_rn(x, 255.0f), 0.5f);      /* no contraction: same value as the host formula */
+    };
+    dst[i] = make_uchar4(q(v.x), q(v.y), q(v.z), q(v.w));
+}
 
 int fail(rtb_ctx* c, int code, const char* fmt, ...) {
     char buf[512];
@@ -300,6 +315,7 @@ void rtb_destroy(rtb_ctx* ctx) {
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->cta_times) cudaFree(ctx->cta_times);
     if (ctx->fb) cudaFree(ctx->fb);
+    if (ctx->fb8) cudaFree(ctx->fb8);
     if (ctx->cube) cudaFree(ctx->cube);
     for (int u = 0; u < 6; u++) if (ctx->tex[u].dev) cudaFree(ctx->tex[u].dev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -497,16 +513,15 @@ int rtb_read_rgba32f(rtb_ctx* ctx, float* dst) {
 
 int rtb_read_rgba8(rtb_ctx* ctx, uint8_t* dst) {
     if (!ctx || !dst) return fail(ctx, RTB_ERR_INVALID, "null argument");
-    size_t n = (size_t)ctx->local_rows * ctx->width * 4;
-    std::vector<float> tmp(n);
-    int rc = rtb_read_rgba32f(ctx, tmp.data());
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->local_rows * ctx->width;
+    if (n == 0) return rtb_sync(ctx);
+    if (!ctx->fb8) CU(cudaMalloc(&ctx->fb8, (size_t)ctx->width * ctx->height * 4));
+    rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const float4*)ctx->fb, (uchar4*)ctx->fb8, n);   /* after the frame, same stream */
+    CU(cudaGetLastError());
+    int rc = rtb_sync(ctx);
     if (rc) return rc;
-    for (size_t i = 0; i < n; i++) {
-        float v = tmp[i];
-        v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);        /* GL unorm8 conversion of the colour buffer; NaN -> 0 */
-        if (!(v == v)) v = 0.f;
-        dst[i] = (uint8_t)(v * 255.0f + 0.5f);
-    }
+    CU(cudaMemcpy(dst, ctx->fb8, n * 4, cudaMemcpyDeviceToHost));
     return RTB_OK;
 }
 

@@ -245,6 +245,6 @@ void GLWrapper::present()
 		rtb_sync(ctx);
 	}
 	rtb_stats st;
-	if (!rtb_get_stats(ctx, &st)) printf("frame %d: kernel %d, %.3f ms\n", frame_index, st.kernel_used, st.kernel_ms);
+	if (!rtb_get_stats(ctx, &st) && (frame_index < 3 || getenv("RT_VERBOSE"))) printf("frame %d: kernel %d, %.3f ms\n", frame_index, st.kernel_used, st.kernel_ms);
 	frame_index++;
 }

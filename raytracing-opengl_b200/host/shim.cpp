@@ -4,6 +4,9 @@
 #include "GLWrapper.h"
 #include "shim_state.h"
 
+#include <chrono>
+#include <cstdio>
+
 struct GLFWwindow {
     GLWrapper* owner = nullptr;
     void* user = nullptr;
@@ -16,6 +19,7 @@ struct GLFWwindow {
 
 namespace {
 long g_frames_presented = 0;
+std::chrono::steady_clock::time_point g_first_present;          /* wall clock of the frame loop (the reference prints FPS, main.cpp:158-174) */
 GLenum g_active_unit = GL_TEXTURE0;
 GLuint g_bound_2d[8] = { 0 };
 }
@@ -26,7 +30,15 @@ GLFWwindow* rtb_shim_create_window(GLWrapper* owner, int frames) {
     w->frames_left = frames < 1 ? 1 : frames;
     return w;
 }
-void rtb_shim_destroy_window(GLFWwindow* w) { delete w; }
+void rtb_shim_destroy_window(GLFWwindow* w) {
+    if (g_frames_presented > 1) {
+        /* frames 2..N: update_scene + update_buffers (host -> device) + draw + present, as the unchanged loop runs them */
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - g_first_present).count();
+        printf("frame loop: %ld frames in %.3f s after the first = %.3f ms per frame, %.1f frames/s\n", g_frames_presented - 1, s,
+               s * 1e3 / (double)(g_frames_presented - 1), (double)(g_frames_presented - 1) / s);
+    }
+    delete w;
+}
 
 extern "C" {
 
@@ -35,6 +47,7 @@ void glfwPollEvents(void) {}
 void glfwSwapInterval(int) {}
 void glfwSwapBuffers(GLFWwindow* w) {
     if (w && w->owner) w->owner->present();
+    if (g_frames_presented == 0) g_first_present = std::chrono::steady_clock::now();
     g_frames_presented++;
     if (w && --w->frames_left <= 0) w->should_close = 1;
 }

@@ -299,3 +299,20 @@ def test_partition_with_empty_ranks_and_tiny_canvases(procedural):
         assert sum(p.shape[0] for p in parts) == h
         assert any(p.shape[0] == 0 for p in parts) == ((h + 3) // 4 < world)
         assert np.array_equal(rtb200.gather_rows(parts, h, world, 4), full)
+
+
+def test_rgba8_readback_is_the_gl_unorm_conversion(procedural):
+    """rtb_read_rgba8 = what glReadPixels returns from the reference's RGBA8 colour buffer (GLWrapper.cpp:127,216):
+    clamp to [0,1], x255, round to nearest — converted on the device, compared with numpy on the float frame."""
+    sc = scenes.synthetic_scene("mini2", 90, 50, 3)
+    gl = rtb200.GLWrapper(90, 50)
+    gl.init_window()
+    try:
+        rtb200.setup_scene(gl, sc, procedural)
+        gl.draw()
+        f = gl.read_pixels()
+        u = gl.read_pixels_u8()
+    finally:
+        gl.stop()
+    want = (np.clip(np.nan_to_num(f, nan=0.0), 0.0, 1.0) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+    assert u.shape == (50, 90, 4) and np.array_equal(u, want)
