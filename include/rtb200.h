@@ -99,7 +99,8 @@ int rtb_set_texture2d(rtb_ctx* ctx, int unit, const uint8_t* pixels, int w, int 
 /* Options: "kernel" (enum rtb_kernel), "strict" (1 = no FMA contraction, IEEE
  * div/sqrt: operation-for-operation the shader's arithmetic; 0 = fast build),
  * "cull" (1 = conservative bounding-sphere reject before the torus solve;
- * result-preserving, reported separately from the roofline), "ctas_per_sm". */
+ * result-preserving, reported separately from the roofline), "ctas_per_sm" (quad kernel), "coop" (0 = switch the
+ * persistent kernel's cooperative drain off: an A/B and test switch, results are identical). */
 int rtb_set_option(rtb_ctx* ctx, const char* key, int value);
 
 /* GLWrapper::draw()  (GLWrapper.h:34; GLWrapper.cpp:155-165): render one frame

@@ -14,6 +14,7 @@
  * Compiled twice: -DRTB_STRICT=1 -DRTB_NS=rtb_strict and -DRTB_STRICT=0 -DRTB_NS=rtb_fast.
  */
 #include <cstdint>
+#include <cstdio>
 #include <cuda_runtime.h>
 #include "rt_scan.cuh"
 #include "rt_launch.h"

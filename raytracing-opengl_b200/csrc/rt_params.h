@@ -62,6 +62,7 @@ struct FrameParams {
     unsigned int* tile_counter; int32_t n_tiles_x, n_tiles_y;
     /* options */
     int32_t cull;
+    int32_t coop;                     /* 1 = cooperative drain (default); 0 = every warp drains alone with serial scans (A/B, tests) */
     /* 1.0f, -0.0f, -1.0f as RUN-TIME values: the packed (f32x2) Durand-Kerner solver builds its separately rounded
      * multiplies and adds from FFMA2 with these operands; ptxas must not be able to fold them (rt_device.cuh, "packed") */
     float k_one, k_neg_zero, k_neg_one;

@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
         const bool active = px >= 0;
         float tm, shadow; int id; vec2 ruv;
 
-        if (!exhausted) {
-            if (!__any_sync(FULL, active)) continue;
+        if (!exhausted || !P.coop) {
+            if (!__any_sync(FULL, active)) { if (exhausted) break; else continue; }     /* (break: only with the cooperative drain switched off) */
             /* ---- steady state: one unified scene scan per warp, each lane its own ray and mode ---- */
             scan_scene<COUNT, false, RTB_PERSIST_GATE>(P, S, jro, jrd, active, job == JOB_SHADOW, jlimit, 0, tm, id, shadow, ruv, cnt);
         } else {
@@ -144,6 +144,15 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
                 const vec3 bro = mk3(J.ro[0], J.ro[1], J.ro[2]), brd = mk3(J.rd[0], J.rd[1], J.rd[2]);
                 float r_tm, r_sh; int r_id; vec2 r_uv;
                 coop_scan<COUNT>(P, S, bro, brd, J.shadow != 0, J.limit, r_tm, r_id, r_sh, r_uv, cnt);
+#ifdef RTB_DEBUG_COOP_CHECK
+                {   /* development: redo the ray with the serial scan on lane 0 and report any difference */
+                    float s_tm, s_sh; int s_id; vec2 s_uv; Counters scratch = {};
+                    scan_scene<false, false, true>(P, S, bro, brd, lane == 0, J.shadow != 0, J.limit, 0, s_tm, s_id, s_sh, s_uv, scratch);
+                    if (lane == 0 && (s_tm != r_tm || s_id != r_id || s_sh != r_sh))
+                        printf("COOP MISMATCH shadow=%d limit=%g ro=(%.9g %.9g %.9g) rd=(%.9g %.9g %.9g): coop tm=%.9g id=%x sh=%g | serial tm=%.9g id=%x sh=%g\n",
+                               J.shadow, J.limit, bro.x, bro.y, bro.z, brd.x, brd.y, brd.z, r_tm, r_id, r_sh, s_tm, s_id, s_sh);
+                }
+#endif
                 if (lane == 0) { DrainResult r = { r_tm, r_id, r_sh, r_uv.x, r_uv.y, { 0, 0, 0 } }; results[j] = r; }
             }
             __syncthreads();

@@ -151,9 +151,10 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
  * the frame drains (rt_persistent.cuh).  Equality with the serial scan: every accept test but one is `t < tmin`
  * with the running minimum, so the serial result is the lexicographic minimum of (t, scan position) over all
  * candidates, which is what the reductions compute (scan position = class rank planes < spheres < quadrics <
- * boxes < tori < rings < lights, then index).  The exception is the degenerate-quadric quirk (accepts t > tmin,
- * rt.frag:541-545): quadrics are therefore resolved between two reductions, 32 at a time, and a round that
- * contains a degenerate candidate is replayed in index order against the running minimum (warp shuffles).
+ * boxes < tori < rings < lights, then index).  Two exceptions, both resolved 32 primitives at a time against the
+ * warp-uniform running minimum and replayed in index order (warp shuffles) when they occur: the degenerate-quadric
+ * quirk (accepts t > tmin, rt.frag:541-545) and boxes whose slab test yields NaN (accepted by `!(tN >= tmin)`,
+ * rt.frag:417-423; after that tmin is NaN and no later class can be accepted, exactly as in the serial scan).
  * Shadow mode is an any-hit against the fixed limit: OR over lanes.  No 2-D textures here (persistent kernel). */
 DEV int scan_rank(int type) {       /* rtb_prim_type -> position of the class in calcInter's order */
     return type == RTB_TYPE_PLANE ? 0 : type == RTB_TYPE_SPHERE ? 1 : type;
@@ -213,9 +214,31 @@ DEV void coop_scan(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, b
             }
         }
     }
-    for (int i = lane; i < P.n_box; i += 32) {
-        if (intersectBox(ro, rd, S.boxes + i, tmin, t)) {
-            if (shadow_mode) occluded = true; else { tmin = t; id = make_id(RTB_TYPE_BOX, i); }
+    if (shadow_mode) {
+        for (int i = lane; i < P.n_box; i += 32)
+            if (intersectBox(ro, rd, S.boxes + i, tmin, t)) occluded = true;
+    } else if (P.n_box > 0) {
+        /* boxes accept with `!(tN >= tmin)`: NaN candidates and a NaN running minimum make the order matter
+         * (box_accept above), so boxes are resolved like quadrics: 32 at a time against the warp-uniform running
+         * minimum, by reduction when no NaN is involved, in index order otherwise */
+        if (P.n_surf == 0) warp_nearest(tmin, id);
+        for (int base = 0; base < P.n_box; base += 32) {
+            const int i = base + lane;
+            float tN = 0.f;
+            const bool valid = i < P.n_box && box_candidate(ro, rd, S.boxes + i, tN);
+            if (!__any_sync(FULL, (valid && tN != tN) || tmin != tmin)) {
+                const bool acc = box_accept(valid, tN, tmin);
+                float ct = acc ? tN : tmin;
+                int cid = acc ? make_id(RTB_TYPE_BOX, i) : id;
+                warp_nearest(ct, cid);
+                tmin = ct; id = cid;
+            } else {
+                for (int l = 0; l < 32; l++) {
+                    const bool v = __shfl_sync(FULL, valid ? 1 : 0, l) != 0;
+                    const float tt = __shfl_sync(FULL, tN, l);
+                    if (box_accept(v, tt, tmin)) { tmin = tt; id = make_id(RTB_TYPE_BOX, base + l); }
+                }
+            }
         }
     }
     const PackK K = make_packk(P);

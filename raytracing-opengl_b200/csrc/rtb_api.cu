@@ -46,7 +46,7 @@ struct rtb_ctx {
     uint8_t* fb8 = nullptr;                       /* RGBA8 copy of the frame, made on demand by rtb_read_rgba8 */
     uint8_t* cube = nullptr; int cube_w = 0, cube_h = 0;
     Tex2D tex[6];
-    int opt_kernel = RTB_KERNEL_AUTO, opt_strict = 0, opt_cull = 0, opt_ctas_per_sm = 0;
+    int opt_kernel = RTB_KERNEL_AUTO, opt_strict = 0, opt_cull = 0, opt_ctas_per_sm = 0, opt_coop = 1;
     rtb_stats stats = {};
     bool timed_pending = false;
     std::string err;
@@ -223,6 +223,7 @@ int do_render(rtb_ctx* ctx, float* target, cudaStream_t st, bool counted, bool t
     P.tile_counter = ctx->tile_counter;
     P.n_tiles_x = (ctx->width + 7) / 8; P.n_tiles_y = (ctx->local_rows + 3) / 4;
     P.cull = ctx->opt_cull;
+    P.coop = ctx->opt_coop;
     P.k_one = 1.0f; P.k_neg_zero = -0.0f; P.k_neg_one = -1.0f;
     P.counters = counted ? ctx->counters : nullptr;
     P.cta_times = nullptr;
@@ -415,6 +416,7 @@ int rtb_set_option(rtb_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "strict")) ctx->opt_strict = value ? 1 : 0;
     else if (!strcmp(key, "cull")) ctx->opt_cull = value ? 1 : 0;
     else if (!strcmp(key, "ctas_per_sm")) ctx->opt_ctas_per_sm = value;
+    else if (!strcmp(key, "coop")) ctx->opt_coop = value ? 1 : 0;
     else return fail(ctx, RTB_ERR_INVALID, "unknown option '%s'", key);
     return RTB_OK;
 }
