@@ -57,6 +57,7 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
     float shadow = 0.f;
     vec2 ring_uv = mk2(0.f, 0.f);
     float t;
+    const PackK K = make_packk(P);
     const bool on = GATE ? active : true;
     if (COUNT && active) { if (shadow_mode) cnt.rays_s++; else cnt.rays_n++; }
 
@@ -91,25 +92,25 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
     }
     for (int i = 0; i < P.n_surf; i++) {
         if (on) {
-            if (intersectSurface(ro, rd, S.surfs + i, tmin, t)) {
+            if (intersectSurface(K, ro, rd, S.surfs + i, tmin, t)) {
                 if (shadow_mode) shadow = 1.f; else { tmin = t; id = make_id(RTB_TYPE_SURFACE, i); }
             }
         }
     }
+#pragma unroll 1
     for (int i = 0; i < P.n_box; i++) {
         if (on) {
-            if (intersectBox(ro, rd, S.boxes + i, tmin, t)) {
+            if (intersectBox(K, ro, rd, S.boxes + i, tmin, t)) {
                 if (shadow_mode) shadow = 1.f; else { tmin = t; id = make_id(RTB_TYPE_BOX, i); }
             }
         }
     }
-    const PackK K = make_packk(P);
     for (int i = 0; i < P.n_torus; i++) {
         if (on) {
             /* intersectTorus, rt.frag:462-487 (a capped loop + straggler queue was tried here and measured SLOWER:
              * trip counts of neighbouring lanes are correlated, lock-step loses only ~19 %) */
             TorusState st;
-            if (torus_setup(ro, rd, S.tori + i, P.cull, st)) {
+            if (torus_setup(K, ro, rd, S.tori + i, P.cull, st)) {
                 int iters;
                 t = RTB_SCALAR_DK ? torus_solve_scalar(st, iters) : torus_solve(K, st, iters);
                 if (COUNT && active) cnt.dk += iters;
@@ -121,7 +122,7 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
     }
     for (int i = 0; i < P.n_ring; i++) {
         vec2 uv = mk2(0.f, 0.f);
-        bool hit = on && intersectRing(ro, rd, S.rings + i, tmin, t, uv);
+        bool hit = on && intersectRing(K, ro, rd, S.rings + i, tmin, t, uv);
         int tex = S.rings[i].tex;
         if (hit && !shadow_mode) { tmin = t; id = make_id(RTB_TYPE_RING, i); ring_uv = uv; }
         if (TEX && tex > 0) {
@@ -175,6 +176,7 @@ template <bool COUNT>
 DEV void coop_scan(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, bool shadow_mode, float limit,
                    float& tmin_out, int& id_out, float& shadow_out, vec2& ring_uv_out, Counters& cnt) {
     const int lane = threadIdx.x & 31;
+    const PackK K = make_packk(P);
     float tmin = limit, t;
     int id = -1;
     bool occluded = false;
@@ -192,14 +194,14 @@ DEV void coop_scan(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, b
     }
     if (shadow_mode) {
         for (int i = lane; i < P.n_surf; i += 32)
-            if (intersectSurface(ro, rd, S.surfs + i, tmin, t)) occluded = true;
+            if (intersectSurface(K, ro, rd, S.surfs + i, tmin, t)) occluded = true;
     } else if (P.n_surf > 0) {
         warp_nearest(tmin, id);                                 /* the running minimum after planes and spheres, on every lane */
         for (int base = 0; base < P.n_surf; base += 32) {
             const int i = base + lane;
             int kind = 0;
             t = 0.f;
-            if (i < P.n_surf) kind = surface_candidate(ro, rd, S.surfs + i, t);
+            if (i < P.n_surf) kind = surface_candidate(K, ro, rd, S.surfs + i, t);
             if (!__any_sync(FULL, kind == 2)) {
                 float ct = surface_accept(kind, t, tmin) ? t : tmin;
                 int cid = surface_accept(kind, t, tmin) ? make_id(RTB_TYPE_SURFACE, i) : id;
@@ -216,7 +218,7 @@ DEV void coop_scan(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, b
     }
     if (shadow_mode) {
         for (int i = lane; i < P.n_box; i += 32)
-            if (intersectBox(ro, rd, S.boxes + i, tmin, t)) occluded = true;
+            if (intersectBox(K, ro, rd, S.boxes + i, tmin, t)) occluded = true;
     } else if (P.n_box > 0) {
         /* boxes accept with `!(tN >= tmin)`: NaN candidates and a NaN running minimum make the order matter
          * (box_accept above), so boxes are resolved like quadrics: 32 at a time against the warp-uniform running
@@ -225,7 +227,7 @@ DEV void coop_scan(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, b
         for (int base = 0; base < P.n_box; base += 32) {
             const int i = base + lane;
             float tN = 0.f;
-            const bool valid = i < P.n_box && box_candidate(ro, rd, S.boxes + i, tN);
+            const bool valid = i < P.n_box && box_candidate(K, ro, rd, S.boxes + i, tN);
             if (!__any_sync(FULL, (valid && tN != tN) || tmin != tmin)) {
                 const bool acc = box_accept(valid, tN, tmin);
                 float ct = acc ? tN : tmin;
@@ -241,10 +243,9 @@ DEV void coop_scan(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, b
             }
         }
     }
-    const PackK K = make_packk(P);
     for (int i = lane; i < P.n_torus; i += 32) {
         TorusState st;
-        if (torus_setup(ro, rd, S.tori + i, P.cull, st)) {
+        if (torus_setup(K, ro, rd, S.tori + i, P.cull, st)) {
             int iters;
             t = RTB_SCALAR_DK ? torus_solve_scalar(st, iters) : torus_solve(K, st, iters);
             if (COUNT) cnt.dk += iters;
@@ -255,7 +256,7 @@ DEV void coop_scan(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, b
     }
     for (int i = lane; i < P.n_ring; i += 32) {
         vec2 uv;
-        if (intersectRing(ro, rd, S.rings + i, tmin, t, uv)) {
+        if (intersectRing(K, ro, rd, S.rings + i, tmin, t, uv)) {
             if (shadow_mode) occluded = true; else { tmin = t; id = make_id(RTB_TYPE_RING, i); ring_uv = uv; }
         }
     }
