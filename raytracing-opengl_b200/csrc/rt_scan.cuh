@@ -112,7 +112,7 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
             TorusState st;
             if (torus_setup(K, ro, rd, S.tori + i, P.cull, st)) {
                 int iters;
-                t = RTB_SCALAR_DK ? torus_solve_scalar(st, iters) : torus_solve(K, st, iters);
+                t = RTB_SCALAR_DK ? torus_solve_scalar(st, iters) : torus_solve<!TEX>(K, st, iters);
                 if (COUNT && active) cnt.dk += iters;
                 if (t > 0 && t < 100 && t < tmin) {
                     if (shadow_mode) shadow = 1.f; else { tmin = t; id = make_id(RTB_TYPE_TORUS, i); }
@@ -247,7 +247,7 @@ DEV void coop_scan(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, b
         TorusState st;
         if (torus_setup(K, ro, rd, S.tori + i, P.cull, st)) {
             int iters;
-            t = RTB_SCALAR_DK ? torus_solve_scalar(st, iters) : torus_solve(K, st, iters);
+            t = RTB_SCALAR_DK ? torus_solve_scalar(st, iters) : torus_solve<true>(K, st, iters);
             if (COUNT) cnt.dk += iters;
             if (t > 0 && t < 100 && t < tmin) {
                 if (shadow_mode) occluded = true; else { tmin = t; id = make_id(RTB_TYPE_TORUS, i); }
