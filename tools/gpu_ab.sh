@@ -1,5 +1,6 @@
 #!/bin/bash
-# Development: GPU parity suite + A/B timings of library variants only.
+# Development (under gpurun): GPU parity suite + A/B timings of the library variants built by tools/build_variant.sh.
+# usage: bash tools/gpu_ab.sh <tag> <variant> [variant ...]   -> gpurun_out/<tag>/{pytest.log,variants.jsonl}
 tag=${1:-rX}; shift
 out=gpurun_out/$tag; mkdir -p $out
 ( time timeout 700 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -40 ) > $out/pytest.log 2>&1

@@ -1,4 +1,5 @@
 #!/bin/bash
+# usage (under gpurun): bash tools/gpu_evidence.sh <tag>   -> gpurun_out/<tag>/...
 # One gpurun call for the round's evidence: parity suite, one full ncu capture (-> summary + profiles/traffic.json), the bench line,
 # the ncu launch list of the same command, the other BASELINE configs, the unchanged main.cpp frame loop.
 tag=${1:-rX}
