@@ -1,6 +1,6 @@
 """Development: parity (strict vs oracle, incl. DK trip counts) + full-size timing of the library named by RTB200_LIB."""
 import os, sys, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import rtb200
 from rtb200 import scenes, textures

@@ -5,6 +5,6 @@ tag=${1:-rX}; shift
 out=gpurun_out/$tag; mkdir -p $out
 ( time timeout 700 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -40 ) > $out/pytest.log 2>&1
 for v in "$@"; do
-  RTB200_LIB=$PWD/build/variants/$v/librtb200.so timeout 300 python tools/variant_check.py --noparity >> $out/variants.jsonl 2>> $out/variants.err
+  RTB200_LIB=$PWD/build/variants/$v/librtb200.so timeout 300 python tests/dev/variant_check.py --noparity >> $out/variants.jsonl 2>> $out/variants.err
 done
 tail -5 $out/pytest.log; cat $out/variants.jsonl
