@@ -123,7 +123,7 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
     for (int i = 0; i < P.n_ring; i++) {
         vec2 uv = mk2(0.f, 0.f);
         bool hit = on && intersectRing(K, ro, rd, S.rings + i, tmin, t, uv);
-        int tex = S.rings[i].tex;
+        int tex = ldsi(S.rings + i, offsetof(PRing, tex));
         if (hit && !shadow_mode) { tmin = t; id = make_id(RTB_TYPE_RING, i); ring_uv = uv; }
         if (TEX && tex > 0) {
             bool site = hit && shadow_mode;
