@@ -16,8 +16,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
-#include "rt_scan.cuh"
 #include "rt_launch.h"
+#include "rt_scan.cuh"
 
 namespace RTB_NS {
 
