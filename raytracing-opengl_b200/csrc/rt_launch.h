@@ -16,16 +16,7 @@
 #define PERSIST_MIN_BLOCKS 1
 #endif
 /* dynamic shared memory of the persistent kernel: staged scene (rounded up to 128 B) + one 32-B job and one 32-B result per thread */
-/* RTB_DK_FLAT=1 (A/B switch, written but NOT yet run on the GPU): per-lane Durand-Kerner schedule (rt_scan.cuh, scan_tori_flat);
- * it adds a ring of RTB_DK_RING_DEPTH 32-byte slots per thread behind the drain area */
-#ifndef RTB_DK_FLAT
-#define RTB_DK_FLAT 0
-#endif
-#ifndef RTB_DK_RING_DEPTH
-#define RTB_DK_RING_DEPTH 2
-#endif
-#define PERSIST_RING_BYTES ((size_t)(RTB_DK_FLAT ? PERSIST_THREADS * RTB_DK_RING_DEPTH * 32 : 0))
-#define PERSIST_SMEM_BYTES(scene_bytes) ((((size_t)(scene_bytes) + 127u) & ~(size_t)127u) + (size_t)PERSIST_THREADS * 64u + PERSIST_RING_BYTES)
+#define PERSIST_SMEM_BYTES(scene_bytes) ((((size_t)(scene_bytes) + 127u) & ~(size_t)127u) + (size_t)PERSIST_THREADS * 64u)
 #define RTB_LAUNCH_QUAD 1
 #define RTB_LAUNCH_PERSISTENT 2
 

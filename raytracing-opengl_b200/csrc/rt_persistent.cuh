@@ -51,9 +51,6 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
     const SceneView S = make_view(smem, P.lay);
     DrainJob* const jobs = (DrainJob*)(smem + ((P.lay.total_bytes + 127u) & ~127u));
     DrainResult* const results = (DrainResult*)(jobs + PERSIST_THREADS);
-#if RTB_DK_FLAT
-    float4* const dk_ring = (float4*)(results + PERSIST_THREADS);                             /* PERSIST_RING_BYTES, rt_launch.h */
-#endif
 
     const int lane = threadIdx.x & 31;
     const unsigned total = (unsigned)(P.n_tiles_x * P.n_tiles_y) * 32u;
@@ -122,11 +119,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
         if (!exhausted || !P.coop) {
             if (!__any_sync(FULL, active)) { if (exhausted) break; else continue; }     /* (break: only with the cooperative drain switched off) */
             /* ---- steady state: one unified scene scan per warp, each lane its own ray and mode ---- */
-            scan_scene<COUNT, false, RTB_PERSIST_GATE>(P, S, jro, jrd, active, job == JOB_SHADOW, jlimit, 0, tm, id, shadow, ruv, cnt
-#if RTB_DK_FLAT
-                                                       , dk_ring
-#endif
-                                                       );
+            scan_scene<COUNT, false, RTB_PERSIST_GATE>(P, S, jro, jrd, active, job == JOB_SHADOW, jlimit, 0, tm, id, shadow, ruv, cnt);
         } else {
             /* ---- drain: the frame has no fresh pixels left, lanes fall idle one by one.  All warps of the CTA pool
              * the scans of their live paths in shared memory and serve them one ray per warp (coop_scan), so the
@@ -154,11 +147,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
 #ifdef RTB_DEBUG_COOP_CHECK
                 {   /* development: redo the ray with the serial scan on lane 0 and report any difference */
                     float s_tm, s_sh; int s_id; vec2 s_uv; Counters scratch = {};
-                    scan_scene<false, false, true>(P, S, bro, brd, lane == 0, J.shadow != 0, J.limit, 0, s_tm, s_id, s_sh, s_uv, scratch
-#if RTB_DK_FLAT
-                                                   , dk_ring
-#endif
-                                                   );
+                    scan_scene<false, false, true>(P, S, bro, brd, lane == 0, J.shadow != 0, J.limit, 0, s_tm, s_id, s_sh, s_uv, scratch);
                     if (lane == 0 && (s_tm != r_tm || s_id != r_id || s_sh != r_sh))
                         printf("COOP MISMATCH shadow=%d limit=%g ro=(%.9g %.9g %.9g) rd=(%.9g %.9g %.9g): coop tm=%.9g id=%x sh=%g | serial tm=%.9g id=%x sh=%g\n",
                                J.shadow, J.limit, bro.x, bro.y, bro.z, brd.x, brd.y, brd.z, r_tm, r_id, r_sh, s_tm, s_id, s_sh);

@@ -43,108 +43,6 @@ DEV Derivs quad_derivs(bool site, int tag, vec2 uv) {
     return d;
 }
 
-#if RTB_DK_FLAT
-/* Per-lane Durand-Kerner schedule (A/B switch RTB_DK_FLAT, persistent kernel only; NOT yet run on the GPU).
- * The lock-step loop runs every trip until the slowest of the 32 solves of a torus is done: 26.2 of 32 lanes are active on average.
- * Here every lane walks its own chain torus 0, 1, 2, ...: when its solve converges it stores the roots and continues with the next
- * torus at once.  What stays lock-step (full warps) is the setup of a torus (two rotations, the loop invariants of cTorus), which runs
- * at most RTB_DK_RING_DEPTH tori ahead of the slowest lane, and the root selection + accept, which runs as soon as every lane is past a
- * torus — in index order per lane, so tmin / id / shadow evolve exactly as in the serial scan.  Setup out and roots back travel
- * through a ring of 32-byte slots per thread in shared memory (slot = four conflict-free 8-byte quarters, thread-private: no barriers).
- * tests/dev/dk_schedule_sim.py: 0.87-0.91 of the lock-step cycles on oracle trip counts at +20..35 issue cycles per trip, depth 2 as
- * good as unbounded.  SASS of this first version: ~95 extra issue cycles per trip (root-copy moves, the store-roots / load-next block,
- * loop control, housekeeping) = break-even; it has to come down to ~45 before the schedule pays. */
-constexpr int DK_CULLED = (int)0xffc0dead;       /* a NaN pattern arithmetic never produces: marks a torus rejected by the "cull" option */
-static_assert((RTB_DK_RING_DEPTH & (RTB_DK_RING_DEPTH - 1)) == 0, "ring depth must be a power of two");
-/* ring slot of torus t = four 8-byte quarters, each an array over the CTA's threads (conflict-free 64-bit accesses):
- *   setup:  (rdrd, rord2) (k0, rdxy) (roxy2, roxy0) (fourR2, mark)        roots:  c0 c1 c2 c3 */
-DEV unsigned ring_slot(unsigned mine, int torus) { return mine + (unsigned)(torus & (RTB_DK_RING_DEPTH - 1)) * (4u * PERSIST_THREADS * 8u); }
-constexpr unsigned RING_Q = PERSIST_THREADS * 8u;
-DEV f2 lds_f2(unsigned a) { f2 r; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r.v) : "r"(a)); return r; }
-DEV void sts_f2(unsigned a, f2 v) { asm volatile("st.shared.b64 [%0], %1;" :: "r"(a), "l"(v.v) : "memory"); }
-struct TorusRayS { float rdrd, rord2, k0, rdxy, roxy2, roxy0, fourR2; };
-DEV TorusRayP broadcast(const TorusRayS& s) {                    /* pk(x, x) of one value compiles to the R.F32 operand form: no instruction */
-    TorusRayP T;
-    T.rdrd = pk(s.rdrd, s.rdrd); T.rord2 = pk(s.rord2, s.rord2); T.rdxy = pk(s.rdxy, s.rdxy); T.roxy2 = pk(s.roxy2, s.roxy2);
-    T.fourR2 = pk(s.fourR2, s.fourR2); T.k0 = s.k0; T.roxy0 = s.roxy0;
-    return T;
-}
-template <bool COUNT>
-DEV void scan_tori_flat(const FrameParams& P, const SceneView& S, const PackK& K, vec3 ro, vec3 rd, bool on, bool active, bool shadow_mode,
-                        float4* ring, float& tmin, int& id, float& shadow, Counters& cnt) {
-    const int n = P.n_torus;
-    unsigned mine;                                               /* this thread's column of the ring, as an opaque shared-space address */
-    { const unsigned a = (unsigned)__cvta_generic_to_shared(ring) + threadIdx.x * 8u; asm volatile("mov.u32 %0, %1;" : "=r"(mine) : "r"(a)); }
-    int produced = 0, retired = 0;                               /* warp-uniform */
-    int cur = on ? 0 : n;                                        /* per lane: tori this lane is done with */
-    bool live = false;
-    int iters = 0;
-    f2 c0 = pk(0.f, 0.f), c1 = c0, c2 = c0, c3 = c0;
-    TorusRayS Ts = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
-    auto acquire = [&]() {                                       /* take torus `cur` (its setup is in the ring) */
-        const unsigned a = ring_slot(mine, cur);
-        const f2 q3 = lds_f2(a + 3u * RING_Q);
-        if (__float_as_int(hi(q3)) == DK_CULLED) { cur++; return; }   /* nothing to solve; the retire step sees the mark */
-        const f2 q0 = lds_f2(a), q1 = lds_f2(a + RING_Q), q2 = lds_f2(a + 2u * RING_Q);
-        Ts.rdrd = lo(q0); Ts.rord2 = hi(q0); Ts.k0 = lo(q1); Ts.rdxy = hi(q1); Ts.roxy2 = lo(q2); Ts.roxy0 = hi(q2); Ts.fourR2 = lo(q3);
-        TorusState st;
-        torus_init_roots(st);
-        c0 = pk(st.c0.x, st.c0.y); c1 = pk(st.c1.x, st.c1.y); c2 = pk(st.c2.x, st.c2.y); c3 = pk(st.c3.x, st.c3.y);
-        iters = 0;
-        live = true;
-    };
-    while (retired < n) {
-        if (__any_sync(FULL, !live)) {
-            const int slowest = __reduce_min_sync(FULL, cur);
-            for (; retired < slowest; retired++) {               /* every lane is past this torus: root selection and accept, rt.frag:478-486 */
-                const unsigned a = ring_slot(mine, retired);
-                const f2 r3 = lds_f2(a + 3u * RING_Q);
-                if (on && __float_as_int(hi(r3)) != DK_CULLED) {
-                    const f2 r0 = lds_f2(a), r1 = lds_f2(a + RING_Q), r2 = lds_f2(a + 2u * RING_Q);
-                    TorusState rs;
-                    rs.c0 = mk2(lo(r0), hi(r0)); rs.c1 = mk2(lo(r1), hi(r1)); rs.c2 = mk2(lo(r2), hi(r2)); rs.c3 = mk2(lo(r3), hi(r3));
-                    const float t = torus_root(rs);
-                    if (t > 0 && t < 100 && t < tmin) {
-                        if (shadow_mode) shadow = 1.f; else { tmin = t; id = make_id(RTB_TYPE_TORUS, retired); }
-                    }
-                }
-            }
-            for (; produced < n && produced < retired + RTB_DK_RING_DEPTH; produced++) {     /* setup of the next torus, all lanes */
-                TorusState st;
-                const bool solve = torus_setup(K, ro, rd, S.tori + produced, P.cull, st);
-                const unsigned a = ring_slot(mine, produced);
-                sts_f2(a, pk(st.T.rdrd, st.T.rord2)); sts_f2(a + RING_Q, pk(st.T.k0, st.T.rdxy)); sts_f2(a + 2u * RING_Q, pk(st.T.roxy2, st.T.roxy0));
-                sts_f2(a + 3u * RING_Q, pk(st.T.fourR2, solve ? 0.f : __int_as_float(DK_CULLED)));
-            }
-            if (!live && cur < produced) acquire();
-        }
-        if (live) {                                              /* one trip, rt.frag:471-477 (torus_solve<true>) */
-            const TorusRayP T = broadcast(Ts);
-            const f2 s0 = c0, s1 = c1, s2 = c2, s3 = c3;
-            DKWitness wt = { CUDART_INF_F, CUDART_INF_F, 0.f, 0.f };
-            DKstep_o(K, c0, c1, c2, c3, T, wt);
-            DKstep_o(K, c1, c2, c3, c0, T, wt);
-            DKstep_o(K, c2, c3, c0, c1, T, wt);
-            DKstep_o(K, c3, c0, c1, c2, T, wt);
-            float e = wt.E;
-            if (!(wt.Wc >= TWO_M50 && wt.Wq >= TWO_M100 && wt.D <= TWO_P125 && e == e)) {
-                const DKTrip g = dk_trip_guarded(K, s0, s1, s2, s3, T);
-                c0 = g.c0; c1 = g.c1; c2 = g.c2; c3 = g.c3; e = g.e;
-            }
-            iters++;
-            if (e < 0.001f || iters >= 60) {                     /* solved: roots into the slot the setup came from */
-                const unsigned a = ring_slot(mine, cur);
-                sts_f2(a, c0); sts_f2(a + RING_Q, c1); sts_f2(a + 2u * RING_Q, c2); sts_f2(a + 3u * RING_Q, c3);
-                if (COUNT && active) cnt.dk += iters;
-                cur++;
-                live = false;
-                if (cur < produced) acquire();
-            }
-        }
-    }
-}
-#endif
-
 /* TEX: 2-D textures may be referenced (quad kernel): textured rings add their alpha to
  * the shadow term (rt.frag:644-651) and need the quad exchange -> scan_scene must then be
  * called from warp-uniform control flow.  ctx = 0 main path / 1 getReflectedColor.
@@ -153,11 +51,7 @@ DEV void scan_tori_flat(const FrameParams& P, const SceneView& S, const PackK& K
  * last ray and the result is dropped, which saves a branch region per primitive. */
 template <bool COUNT, bool TEX, bool GATE>
 DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, bool active, bool shadow_mode, float limit, int ctx,
-                    float& tmin_out, int& id_out, float& shadow_out, vec2& ring_uv_out, Counters& cnt
-#if RTB_DK_FLAT
-                    , float4* dk_ring = nullptr
-#endif
-                    ) {
+                    float& tmin_out, int& id_out, float& shadow_out, vec2& ring_uv_out, Counters& cnt) {
     float tmin = limit;
     int id = -1;
     float shadow = 0.f;
@@ -211,14 +105,12 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
             }
         }
     }
-#if RTB_DK_FLAT && RTB_STRICT
-    if constexpr (!TEX) scan_tori_flat<COUNT>(P, S, K, ro, rd, on, active, shadow_mode, dk_ring, tmin, id, shadow, cnt);
-    else
-#endif
     for (int i = 0; i < P.n_torus; i++) {
         if (on) {
-            /* intersectTorus, rt.frag:462-487 (a capped loop + straggler queue was tried here and measured SLOWER:
-             * trip counts of neighbouring lanes are correlated, lock-step loses only ~19 %) */
+            /* intersectTorus, rt.frag:462-487.  Lock-step over the warp keeps 26 of 32 lanes busy in the trips.  Tried: a capped loop +
+             * straggler queue (measured slower), and a per-lane schedule through a shared-memory ring (every lane walks its own chain of
+             * solves): its store-roots / load-next block and loop control cost ~80 issue cycles per trip in the SASS, more than the idle
+             * lanes it removes in an issue-bound kernel (tests/dev/dk_schedule_sim.py) */
             TorusState st;
             if (torus_setup(K, ro, rd, S.tori + i, P.cull, st)) {
                 int iters;
