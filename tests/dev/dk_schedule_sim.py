@@ -11,8 +11,9 @@ Cycle constants from the round-1b SASS: C_TRIP = 300 (264 FP + 36 other), C_TORU
 
 usage: python tests/dev/dk_schedule_sim.py [n_primary_rays]      (about 1 minute for 1200)
 Result of 2026-10 (3483 rays): lock-step lane utilisation 0.74 in this sample (ncu on the real frame: 0.82 — real warps are more
-coherent); flattened D=2..8, OVH 20: 0.87 of the lock-step cycles, OVH 35: 0.91.  Scaled to the measured 0.82 this is -5 .. -7 % of the
-frame; a ring of depth 2 is as good as an unbounded one.
+coherent); flattened D=2..8, OVH 20: 0.87 of the lock-step cycles, OVH 35: 0.91; a ring of depth 2 is as good as an unbounded one.
+The implementation that was then written needed OVH ~ 95 in its SASS (floor by hand count ~ 80), i.e. break-even at the measured 0.82:
+the schedule was dropped.  Set OVH to what a new idea costs before writing it.
 """
 import os
 import sys
