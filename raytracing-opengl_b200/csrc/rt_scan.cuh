@@ -47,8 +47,9 @@ DEV Derivs quad_derivs(bool site, int tag, vec2 uv) {
  * the shadow term (rt.frag:644-651) and need the quad exchange -> scan_scene must then be
  * called from warp-uniform control flow.  ctx = 0 main path / 1 getReflectedColor.
  * GATE: lanes with active == false skip the tests (quad kernel: dead paths and helper lanes are common).
- * The persistent kernel passes GATE = false: idle lanes exist only while the frame drains, they re-scan their
- * last ray and the result is dropped, which saves a branch region per primitive. */
+ * The persistent kernel passes RTB_PERSIST_GATE (default true: measured faster when it was introduced, before the cooperative
+ * drain existed).  With the cooperative drain idle lanes exist only in the last trips of a frame; GATE = false would let them
+ * re-scan their last ray (result dropped) and save the 4-instruction branch region per test: an A/B candidate, DESIGN.md section 8. */
 template <bool COUNT, bool TEX, bool GATE>
 DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, bool active, bool shadow_mode, float limit, int ctx,
                     float& tmin_out, int& id_out, float& shadow_out, vec2& ring_uv_out, Counters& cnt) {
