@@ -84,12 +84,21 @@ def _make_desc(scene, textures, keep):
     return d
 
 
-class Oracle:
-    """One scene loaded into the restated oracle (impl='oracle') or into the compiled reference shader (impl='ref')."""
+PRECISIONS = {"f32": "orc", "f64": "orc64", "sr": "orcsr"}
 
-    def __init__(self, scene, textures=None, impl: str = "oracle"):
+
+class Oracle:
+    """One scene loaded into the restated oracle (impl='oracle') or into the compiled reference shader (impl='ref').
+
+    precision (restatement only, oracle/real_types.h): "f32" = the pinned fp32 restatement, "f64" = the same control flow in
+    double, "sr" = fp32 with stochastic rounding (render_ex(sample=k) selects the k-th random-rounding stream)."""
+
+    def __init__(self, scene, textures=None, impl: str = "oracle", precision: str = "f32"):
         self.impl = impl
-        self.p = "orc" if impl == "oracle" else "ref"
+        self.precision = precision
+        if impl != "oracle" and precision != "f32":
+            raise ValueError("oracle/_ref exists in fp32 only")
+        self.p = PRECISIONS[precision] if impl == "oracle" else "ref"
         path = LIB_ORACLE if impl == "oracle" else LIB_REF
         if not os.path.isfile(path):
             raise FileNotFoundError(f"{path} not built (make -C oracle{' ref' if impl == 'ref' else ''})")
@@ -103,11 +112,14 @@ class Oracle:
         getattr(L, p + "_in_shadow").restype = C.c_float
         getattr(L, p + "_in_shadow").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
         if impl == "oracle":
-            L.orc_render.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.POINTER(Stats), C.c_int]
-            L.orc_render_quads.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Stats), C.c_int]
-            L.orc_set_pairing.argtypes = [C.c_void_p, C.c_int]
-            L.orc_intersect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
-            L.orc_ray_dir.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+            getattr(L, p + "_render").argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.POINTER(Stats), C.c_int]
+            getattr(L, p + "_render_quads").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Stats), C.c_int]
+            getattr(L, p + "_render_ex").argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(Stats), C.c_int]
+            getattr(L, p + "_render_quads_ex").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                           C.POINTER(Stats), C.c_int]
+            getattr(L, p + "_set_pairing").argtypes = [C.c_void_p, C.c_int]
+            getattr(L, p + "_intersect").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+            getattr(L, p + "_ray_dir").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
             L.orc_sample_cube.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
             L.orc_sample_2d.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
             L.orc_mip_levels.argtypes = [C.c_void_p, C.c_int]
@@ -137,7 +149,7 @@ class Oracle:
 
     def set_pairing(self, rule: int):
         if self.impl == "oracle":
-            self.lib.orc_set_pairing(self.h, rule)
+            getattr(self.lib, self.p + "_set_pairing")(self.h, rule)
 
     def render(self, x0=0, y0=0, w=None, h=None, threads=0, stats: Stats | None = None) -> np.ndarray:
         """RGBA32F [h, w, 4]; row 0 = bottom scanline (GL window coordinates)."""
@@ -145,7 +157,7 @@ class Oracle:
         h = self.height if h is None else h
         out = np.empty((h, w, 4), dtype=np.float32)
         if self.impl == "oracle":
-            rc = self.lib.orc_render(self.h, x0, y0, w, h, out.ctypes.data, C.byref(stats) if stats is not None else None, threads)
+            rc = getattr(self.lib, self.p + "_render")(self.h, x0, y0, w, h, out.ctypes.data, C.byref(stats) if stats is not None else None, threads)
         else:
             rc = self.lib.ref_render(self.h, x0, y0, w, h, out.ctypes.data, threads)
         if rc != 0:
@@ -158,11 +170,35 @@ class Oracle:
         qy = np.ascontiguousarray(qy, dtype=np.int32)
         out = np.empty((len(qx), 4, 4), dtype=np.float32)
         if self.impl == "oracle":
-            self.lib.orc_render_quads(self.h, len(qx), qx.ctypes.data, qy.ctypes.data, out.ctypes.data,
-                                      C.byref(stats) if stats is not None else None, threads)
+            getattr(self.lib, self.p + "_render_quads")(self.h, len(qx), qx.ctypes.data, qy.ctypes.data, out.ctypes.data,
+                                                        C.byref(stats) if stats is not None else None, threads)
         else:
             self.lib.ref_render_quads(self.h, len(qx), qx.ctypes.data, qy.ctypes.data, out.ctypes.data, threads)
         return out
+
+    def render_ex(self, x0=0, y0=0, w=None, h=None, sample=0, threads=0, stats: Stats | None = None):
+        """(RGBA32F [h, w, 4], path hash uint64 [h, w], Durand-Kerner trips uint32 [h, w]) — restatement only."""
+        w = self.width if w is None else w
+        h = self.height if h is None else h
+        out = np.empty((h, w, 4), dtype=np.float32)
+        path = np.empty((h, w), dtype=np.uint64)
+        dk = np.empty((h, w), dtype=np.uint32)
+        rc = getattr(self.lib, self.p + "_render_ex")(self.h, x0, y0, w, h, out.ctypes.data, path.ctypes.data, dk.ctypes.data, sample,
+                                                     C.byref(stats) if stats is not None else None, threads)
+        if rc != 0:
+            raise ValueError("render window must be even-aligned and non-empty")
+        return out, path, dk
+
+    def render_quads_ex(self, qx, qy, sample=0, threads=0, stats: Stats | None = None):
+        """([n, 4, 4] colours, [n, 4] path hashes, [n, 4] Durand-Kerner trips) — restatement only."""
+        qx = np.ascontiguousarray(qx, dtype=np.int32)
+        qy = np.ascontiguousarray(qy, dtype=np.int32)
+        out = np.empty((len(qx), 4, 4), dtype=np.float32)
+        path = np.empty((len(qx), 4), dtype=np.uint64)
+        dk = np.empty((len(qx), 4), dtype=np.uint32)
+        getattr(self.lib, self.p + "_render_quads_ex")(self.h, len(qx), qx.ctypes.data, qy.ctypes.data, out.ctypes.data, path.ctypes.data,
+                                                       dk.ctypes.data, sample, C.byref(stats) if stats is not None else None, threads)
+        return out, path, dk
 
     def calc_inter(self, ro, rd, num=0, type_=0):
         ro = np.ascontiguousarray(ro, dtype=np.float32)
@@ -181,12 +217,12 @@ class Oracle:
         ro = np.ascontiguousarray(ro, dtype=np.float32)
         rd = np.ascontiguousarray(rd, dtype=np.float32)
         t, k = C.c_float(0), C.c_int32(0)
-        hit = self.lib.orc_intersect(self.h, type_, index, ro.ctypes.data, rd.ctypes.data, tmin, C.byref(t), C.byref(k))
+        hit = getattr(self.lib, self.p + "_intersect")(self.h, type_, index, ro.ctypes.data, rd.ctypes.data, tmin, C.byref(t), C.byref(k))
         return bool(hit), float(t.value), int(k.value)
 
     def ray_dir(self, x, y):
         out = np.empty(3, dtype=np.float32)
-        self.lib.orc_ray_dir(self.h, x, y, out.ctypes.data)
+        getattr(self.lib, self.p + "_ray_dir")(self.h, x, y, out.ctypes.data)
         return out
 
     def sample_cube(self, d):

@@ -16,6 +16,12 @@
  * Texel filtering (gl_sampler.h) is driver-defined in the reference: parity
  * unpinned there.
  *
+ * PRECISION VARIANTS: the arithmetic is written on the type `real` (real_types.h).  ORC_VARIANT 0 (float) is the
+ * restatement proper and the only one that is pinned; variants 1 (double, orc64_*) and 2 (stochastic rounding,
+ * orcsr_*) run the same control flow and classify pixels whose colour the fp32 arithmetic does not determine.
+ * Every pixel also reports its discrete path (hash of the hit-id / shadow-outcome sequence) and its Durand-Kerner
+ * trip total through the *_ex entry points.
+ *
  * Pins for behaviour the GLSL leaves undefined (SURVEY.md 8a "quirks"):
  *   Q1  `int num, type;` in getReflectedColor (rt.frag:791) are uninitialised and
  *       read after a miss (rt.frag:793): pinned to 0 (=> never TYPE_POINT_LIGHT).
@@ -30,6 +36,7 @@
  */
 #include "rt_oracle.h"
 #include "gl_sampler.h"
+#include "real_types.h"      /* `real` = float (this file's pinned form), double or stochastically rounded fp32: see there */
 
 #include <atomic>
 #include <cfloat>
@@ -43,67 +50,67 @@
 namespace {
 
 constexpr int MAX_GLASS_EVENTS = 64;
-constexpr float PI_F = 3.14159265358979f;      /* rt.frag:5 */
-constexpr float maxDist = 1000000.0f;          /* rt.frag:145 */
+constexpr real PI_F = 3.14159265358979f;      /* rt.frag:5 */
+constexpr real maxDist = 1000000.0f;          /* rt.frag:145 */
 
 /* ---------------- GLSL vector types and built-ins ---------------- */
-struct vec2 { float x, y; };
-struct vec3 { float x, y, z; };
-struct vec4 { float x, y, z, w; };
+struct vec2 { real x, y; };
+struct vec3 { real x, y, z; };
+struct vec4 { real x, y, z, w; };
 
 inline vec2 operator+(vec2 a, vec2 b) { return { a.x + b.x, a.y + b.y }; }
 inline vec2 operator-(vec2 a, vec2 b) { return { a.x - b.x, a.y - b.y }; }
-inline vec2 operator*(vec2 a, float s) { return { a.x * s, a.y * s }; }
-inline vec2 operator*(float s, vec2 a) { return { s * a.x, s * a.y }; }
-inline vec2 operator/(vec2 a, float s) { return { a.x / s, a.y / s }; }
+inline vec2 operator*(vec2 a, real s) { return { a.x * s, a.y * s }; }
+inline vec2 operator*(real s, vec2 a) { return { s * a.x, s * a.y }; }
+inline vec2 operator/(vec2 a, real s) { return { a.x / s, a.y / s }; }
 
 inline vec3 operator+(vec3 a, vec3 b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
 inline vec3 operator-(vec3 a, vec3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
 inline vec3 operator-(vec3 a) { return { -a.x, -a.y, -a.z }; }
 inline vec3 operator*(vec3 a, vec3 b) { return { a.x * b.x, a.y * b.y, a.z * b.z }; }
-inline vec3 operator*(vec3 a, float s) { return { a.x * s, a.y * s, a.z * s }; }
-inline vec3 operator*(float s, vec3 a) { return { s * a.x, s * a.y, s * a.z }; }
-inline vec3 operator/(vec3 a, float s) { return { a.x / s, a.y / s, a.z / s }; }
-inline vec3 operator/(float s, vec3 a) { return { s / a.x, s / a.y, s / a.z }; }
+inline vec3 operator*(vec3 a, real s) { return { a.x * s, a.y * s, a.z * s }; }
+inline vec3 operator*(real s, vec3 a) { return { s * a.x, s * a.y, s * a.z }; }
+inline vec3 operator/(vec3 a, real s) { return { a.x / s, a.y / s, a.z / s }; }
+inline vec3 operator/(real s, vec3 a) { return { s / a.x, s / a.y, s / a.z }; }
 inline vec3& operator+=(vec3& a, vec3 b) { a = a + b; return a; }
 inline vec3& operator*=(vec3& a, vec3 b) { a = a * b; return a; }
-inline vec3& operator*=(vec3& a, float s) { a = a * s; return a; }
+inline vec3& operator*=(vec3& a, real s) { a = a * s; return a; }
 
-inline vec4 operator*(vec4 a, float s) { return { a.x * s, a.y * s, a.z * s, a.w * s }; }
+inline vec4 operator*(vec4 a, real s) { return { a.x * s, a.y * s, a.z * s, a.w * s }; }
 inline bool operator!=(vec4 a, vec4 b) { return a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w; }
 
-inline float gmin(float x, float y) { return (y < x) ? y : x; }           /* GLSL min */
-inline float gmax(float x, float y) { return (x < y) ? y : x; }           /* GLSL max */
-inline float clampf(float x, float lo, float hi) { return gmin(gmax(x, lo), hi); }
-inline float dot(vec2 a, vec2 b) { return a.x * b.x + a.y * b.y; }
-inline float dot(vec3 a, vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-inline float dot(vec4 a, vec4 b) { return (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w); }
-inline float inversesqrt(float x) { return 1.0f / sqrtf(x); }
-inline float length(vec3 v) { return sqrtf(dot(v, v)); }
+inline real gmin(real x, real y) { return (y < x) ? y : x; }           /* GLSL min */
+inline real gmax(real x, real y) { return (x < y) ? y : x; }           /* GLSL max */
+inline real clampf(real x, real lo, real hi) { return gmin(gmax(x, lo), hi); }
+inline real dot(vec2 a, vec2 b) { return a.x * b.x + a.y * b.y; }
+inline real dot(vec3 a, vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline real dot(vec4 a, vec4 b) { return (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w); }
+inline real inversesqrt(real x) { return 1.0f / r_sqrt(x); }
+inline real length(vec3 v) { return r_sqrt(dot(v, v)); }
 inline vec3 normalize(vec3 v) { return v * inversesqrt(dot(v, v)); }
 inline vec2 normalize(vec2 v) { return v * inversesqrt(dot(v, v)); }
 inline vec3 reflect(vec3 I, vec3 N) { return I - N * dot(N, I) * 2.0f; }
-inline vec3 refract(vec3 I, vec3 N, float eta) {
-    float d = dot(N, I);
-    float k = 1.0f - eta * eta * (1.0f - d * d);
-    if (k >= 0.0f) return eta * I - (eta * d + sqrtf(k)) * N;
+inline vec3 refract(vec3 I, vec3 N, real eta) {
+    real d = dot(N, I);
+    real k = 1.0f - eta * eta * (1.0f - d * d);
+    if (k >= 0.0f) return eta * I - (eta * d + r_sqrt(k)) * N;
     return { 0.0f, 0.0f, 0.0f };
 }
-inline float signf(float x) { return (float)((0.0f < x) - (x < 0.0f)); }
-inline float stepf(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
-inline vec3 vabs(vec3 a) { return { fabsf(a.x), fabsf(a.y), fabsf(a.z) }; }
+inline real signf(real x) { return (real)((0.0f < x) - (x < 0.0f)); }
+inline real stepf(real edge, real x) { return x < edge ? 0.0f : 1.0f; }
+inline vec3 vabs(vec3 a) { return { r_abs(a.x), r_abs(a.y), r_abs(a.z) }; }
 inline vec3 vmax(vec3 a, vec3 b) { return { gmax(a.x, b.x), gmax(a.y, b.y), gmax(a.z, b.z) }; }
-inline vec3 vexp(vec3 a) { return { expf(a.x), expf(a.y), expf(a.z) }; }
+inline vec3 vexp(vec3 a) { return { r_exp(a.x), r_exp(a.y), r_exp(a.z) }; }
 inline vec3 v3(const float* p) { return { p[0], p[1], p[2] }; }
 inline vec4 v4(const float* p) { return { p[0], p[1], p[2], p[3] }; }
 inline vec3 xyz(vec4 a) { return { a.x, a.y, a.z }; }
 
 /* hit_record, rt.frag:115-120 (material fields used by the shader only) */
-struct Material { vec3 color, absorb; float diffuse, reflection, refraction; int specular; float kd, ks; };
+struct Material { vec3 color, absorb; real diffuse, reflection, refraction; int specular; real kd, ks; };
 inline Material mat_of(const rtb_material& m) {
     return { v3(m.color), v3(m.absorb), m.diffuse, m.reflect, m.refract, m.specular, m.kd, m.ks };
 }
-struct HitRecord { Material mat; vec3 normal; float bias_mult; float alpha; };
+struct HitRecord { Material mat; vec3 normal; real bias_mult; real alpha; };
 
 /* ---------------- scene ---------------- */
 struct Scene {
@@ -124,8 +131,8 @@ struct Scene {
     int pairing = ORC_PAIR_PROGRAM_ORDER;
 };
 
-/* GLWrapper::to_string, GLWrapper.cpp:279-282: std::to_string(float) == "%f", then
- * parsed by the GLSL compiler as a float literal. */
+/* GLWrapper::to_string, GLWrapper.cpp:279-282: std::to_string(real) == "%f", then
+ * parsed by the GLSL compiler as a real literal. */
 float round_through_percent_f(float v) {
     char buf[64];
     snprintf(buf, sizeof buf, "%f", v);
@@ -152,7 +159,7 @@ struct Frag {
     Stats* st;
     QuadCtx* quad;          /* may be null (KAT entry points): derivatives are 0 */
     int lane = 0;
-    float fragx = 0.5f, fragy = 0.5f;   /* gl_FragCoord.xy */
+    real fragx = 0.5f, fragy = 0.5f;   /* gl_FragCoord.xy */
 
     /* globals of the shader, rt.frag:148-149 */
     vec3 opt_normal = { 0, 0, 0 };
@@ -162,6 +169,10 @@ struct Frag {
     int k_trip = 0, k_ctx = 0, k_stage = 0, k_light = 0, k_ring = 0;
     int ord[3] = { 0, 0, 0 };
     int last_dk = 0;
+    /* discrete path of this invocation: FNV-1a over (type, num) of every calcInter result and the occlusion outcome of every inShadow */
+    uint64_t path = 1469598103934665603ull;
+    uint32_t dk_pix = 0;
+    void path_mix(uint32_t v) { path = (path ^ v) * 1099511628211ull; }
 
     Frag(const Scene& s, Stats* stats, QuadCtx* q) : S(s), st(stats), quad(q) {}
 
@@ -175,17 +186,18 @@ struct Frag {
         Derivs d = { 0, 0, 0, 0 };
         if (!quad) return d;
         uint64_t key = site_key(kind, fetch);
-        quad->cur[lane].push_back({ key, uv.x, uv.y });
+        const float fu = to_f(uv.x), fv = to_f(uv.y);
+        quad->cur[lane].push_back({ key, fu, fv });
         auto find = [&](int other, float& u, float& v) {
             for (const SiteRec& r : quad->prev[other]) if (r.key == key) { u = r.u; v = r.v; return true; }
             return false;
         };
         float u, v;
         if (find(lane ^ 1, u, v)) {     /* dFdx = right - left */
-            if (lane & 1) { d.dudx = uv.x - u; d.dvdx = uv.y - v; } else { d.dudx = u - uv.x; d.dvdx = v - uv.y; }
+            if (lane & 1) { d.dudx = fu - u; d.dvdx = fv - v; } else { d.dudx = u - fu; d.dvdx = v - fv; }
         }
         if (find(lane ^ 2, u, v)) {     /* dFdy = top - bottom */
-            if (lane & 2) { d.dudy = uv.x - u; d.dvdy = uv.y - v; } else { d.dudy = u - uv.x; d.dvdy = v - uv.y; }
+            if (lane & 2) { d.dudy = fu - u; d.dvdy = fv - v; } else { d.dudy = u - fu; d.dvdy = v - fv; }
         }
         return d;
     }
@@ -210,8 +222,8 @@ struct Frag {
 
     /* rt.frag:313-317 */
     vec3 getRayDir() {
-        vec2 half = vec2{ (float)S.scene.canvas_width, (float)S.scene.canvas_height } / 2.0f;
-        vec2 p = (vec2{ fragx, fragy } - half) / (float)S.scene.canvas_height;
+        vec2 half = vec2{ (real)S.scene.canvas_width, (real)S.scene.canvas_height } / 2.0f;
+        vec2 p = (vec2{ fragx, fragy } - half) / (real)S.scene.canvas_height;
         vec3 result = { p.x, p.y, 1.0f };
         return normalize(rotate(v4(S.scene.quat_camera_rotation), result));
     }
@@ -219,36 +231,36 @@ struct Frag {
     /* rt.frag:319-340 */
     vec4 getSphereTexture(vec3 sphereNormal, vec4 quat, int texNum) {
         if (quat != vec4{ 0, 0, 0, 1 }) sphereNormal = rotate(quat, sphereNormal);
-        float u = 0.5f + atan2f(sphereNormal.z, sphereNormal.x) / (2.f * PI_F);
-        float v = 0.5f - asinf(sphereNormal.y) / PI_F;
+        real u = 0.5f + r_atan2(sphereNormal.z, sphereNormal.x) / (2.f * PI_F);
+        real v = 0.5f - r_asin(sphereNormal.y) / PI_F;
         vec2 uv = { u, v };
         Derivs d = site_derivs(SITE_SPHERE, 0, uv);
-        vec2 df = { fabsf(d.dudx) + fabsf(d.dudy), fabsf(d.dvdx) + fabsf(d.dvdy) };   /* fwidth */
+        vec2 df = { r_abs(d.dudx) + r_abs(d.dudy), r_abs(d.dvdx) + r_abs(d.dvdy) };   /* fwidth */
         if (df.x > 0.5f) df.x = 0.f;
         vec4 color = { 0, 0, 0, 0 };
         if (texNum >= 1 && texNum <= 3) {
-            glsim::rgba c = glsim::texture_lod(S.tex[texNum], uv.x, uv.y, log2f(gmax(df.x, df.y) * 1024.f));
+            glsim::rgba c = glsim::texture_lod(S.tex[texNum], to_f(uv.x), to_f(uv.y), to_f(r_log2(gmax(df.x, df.y) * 1024.f)));
             color = { c.r, c.g, c.b, c.a };
         }
         return color;
     }
 
     /* rt.frag:342-354 */
-    bool intersectSphere(vec3 ro, vec3 rd, vec4 object, bool hollow, float tmin, float& t) {
+    bool intersectSphere(vec3 ro, vec3 rd, vec4 object, bool hollow, real tmin, real& t) {
         vec3 oc = ro - xyz(object);
-        float b = dot(oc, rd);
-        float c = dot(oc, oc) - object.w * object.w;
-        float h = b * b - c;
+        real b = dot(oc, rd);
+        real c = dot(oc, oc) - object.w * object.w;
+        real h = b * b - c;
         if (h < 0.0f) return false;
-        float h_sqrt = sqrtf(h);
+        real h_sqrt = r_sqrt(h);
         t = -b - h_sqrt;
         if (hollow && t < 0.0f) t = -b + h_sqrt;
         return t > 0 && t < tmin;
     }
 
     /* rt.frag:356-370, PLANE_ONESIDE defined (rt.frag:21) */
-    bool intersectPlane(vec3 ro, vec3 rd, vec3 n, vec3 p, float tmin, float& t) {
-        float denom = clampf(dot(n, rd), -1, 1);
+    bool intersectPlane(vec3 ro, vec3 rd, vec3 n, vec3 p, real tmin, real& t) {
+        real denom = clampf(dot(n, rd), -1, 1);
         if (denom < -1e-6f) {
             vec3 p_ro = p - ro;
             t = dot(p_ro, n) / denom;
@@ -258,17 +270,17 @@ struct Frag {
     }
 
     /* rt.frag:372-390 */
-    bool intersectRing(vec3 ro, vec3 rd, int num, float tmin, float& t) {
+    bool intersectRing(vec3 ro, vec3 rd, int num, real tmin, real& t) {
         const rtb_ring& ring = S.rings[num];
         vec4 q = v4(ring.quat_rotation);
         rd = rotate(q, rd);
         ro = rotate(q, ro - v3(ring.pos));
         t = -ro.z / rd.z;
-        float x = ro.x + rd.x * t;
-        float y = ro.y + rd.y * t;
-        float p = x * x + y * y;
+        real x = ro.x + rd.x * t;
+        real y = ro.y + rd.y * t;
+        real p = x * x + y * y;
         if (t > 0 && t < tmin && p < ring.r2 && p > ring.r1) {
-            float cosv = dot(normalize(vec2{ x, y }), vec2{ 1, 0 });
+            real cosv = dot(normalize(vec2{ x, y }), vec2{ 1, 0 });
             opt_uv = { (p - ring.r1) / (ring.r2 - ring.r1), cosv };
             return true;
         }
@@ -280,12 +292,12 @@ struct Frag {
     vec4 getRingTexture(int /*num*/, vec2 uv) {
         Derivs d = site_derivs(SITE_RING, 0, uv);
         float lod = glsim::implicit_lod(S.tex[4], d.dudx, d.dvdx, d.dudy, d.dvdy);
-        glsim::rgba c = glsim::texture_lod(S.tex[4], uv.x, uv.y, lod);
+        glsim::rgba c = glsim::texture_lod(S.tex[4], to_f(uv.x), to_f(uv.y), lod);
         return { c.r, c.g, c.b, c.a };
     }
 
     /* rt.frag:399-427 */
-    bool intersectBox(vec3 ro, vec3 rd, int num, float tmin, float& t) {
+    bool intersectBox(vec3 ro, vec3 rd, int num, real tmin, real& t) {
         const rtb_box& box = S.boxes[num];
         vec4 q = v4(box.quat_rotation);
         vec3 rdd = rotate(q, rd);
@@ -295,8 +307,8 @@ struct Frag {
         vec3 k = vabs(m) * v3(box.form);
         vec3 t1 = -n - k;
         vec3 t2 = -n + k;
-        float tN = gmax(gmax(t1.x, t1.y), t1.z);
-        float tF = gmin(gmin(t2.x, t2.y), t2.z);
+        real tN = gmax(gmax(t1.x, t1.y), t1.z);
+        real tF = gmin(gmin(t2.x, t2.y), t2.z);
         if (tN > tF || tF < 0.0f) return false;
         if (tN >= tmin) return false;
         /* nor = -sign(rdd)*step(t1.yzx,t1.xyz)*step(t1.zxy,t1.xyz) */
@@ -319,12 +331,12 @@ struct Frag {
         vec2 uv1 = { 0.5f * (pt.z - pos.z) - 0.5f, 0.5f * (pt.x - pos.x) - 0.5f };   /* pt.zx */
         vec2 uv2 = { 0.5f * (pt.x - pos.x) - 0.5f, 0.5f * (pt.y - pos.y) - 0.5f };   /* pt.xy */
         vec2 uvs[3] = { uv0, uv1, uv2 };
-        float wgt[3] = { fabsf(normal.x), fabsf(normal.y), fabsf(normal.z) };
+        real wgt[3] = { r_abs(normal.x), r_abs(normal.y), r_abs(normal.z) };
         vec4 acc = { 0, 0, 0, 0 };
         for (int f = 0; f < 3; f++) {
             Derivs d = site_derivs(SITE_BOX, f, uvs[f]);
             float lod = glsim::implicit_lod(S.tex[5], d.dudx, d.dvdx, d.dudy, d.dvdy);
-            glsim::rgba c = glsim::texture_lod(S.tex[5], uvs[f].x, uvs[f].y, lod);
+            glsim::rgba c = glsim::texture_lod(S.tex[5], to_f(uvs[f].x), to_f(uvs[f].y), lod);
             vec4 term = { wgt[f] * c.r, wgt[f] * c.g, wgt[f] * c.b, wgt[f] * c.a };
             if (f == 0) acc = term;
             else acc = { acc.x + term.x, acc.y + term.y, acc.z + term.z, acc.w + term.w };
@@ -336,8 +348,8 @@ struct Frag {
     static vec2 cmul(vec2 c1, vec2 c2) { return { c1.x * c2.x - c1.y * c2.y, c1.x * c2.y + c1.y * c2.x }; }
     static vec2 cinv(vec2 c) { return vec2{ c.x, -c.y } / dot(c, c); }
     static vec2 cTorus(vec2 t, vec3 ro, vec3 rd, vec2 torus) {
-        float R2 = torus.x * torus.x;
-        float r2 = torus.y * torus.y;
+        real R2 = torus.x * torus.x;
+        real r2 = torus.y * torus.y;
         vec2 t2 = { t.x * t.x - t.y * t.y, 2.f * t.x * t.y };
         vec2 res = t2 * dot(rd, rd) + 2.f * t * dot(ro, rd) + vec2{ dot(ro, ro) + R2 - r2, 0.f };
         res = cmul(res, res);
@@ -345,14 +357,14 @@ struct Frag {
         vec2 res2 = 4.f * R2 * (t2 * dot(rdxy, rdxy) + 2.f * t * dot(roxy, rdxy) + vec2{ dot(roxy, roxy), 0.f });
         return res - res2;
     }
-    static float DKstep(vec2& c0, vec2 c1, vec2 c2, vec2 c3, vec3 ro, vec3 rd, vec2 torus) {
+    static real DKstep(vec2& c0, vec2 c1, vec2 c2, vec2 c3, vec3 ro, vec3 rd, vec2 torus) {
         vec2 fc = cTorus(c0, ro, rd, torus);
         fc = cmul(fc, cinv(cmul(c0 - c1, cmul(c0 - c2, c0 - c3))));
         c0 = c0 - fc;
-        return gmax(fabsf(fc.x), fabsf(fc.y));
+        return gmax(r_abs(fc.x), r_abs(fc.y));
     }
-    bool intersectTorus(vec3 ro, vec3 rd, int num, float tmin, float& t) {
-        float eps = 0.001f;
+    bool intersectTorus(vec3 ro, vec3 rd, int num, real tmin, real& t) {
+        real eps = 0.001f;
         const rtb_torus& torus = S.toruses[num];
         vec4 q = v4(torus.quat_rotation);
         vec2 form = { torus.form[0], torus.form[1] };
@@ -365,16 +377,17 @@ struct Frag {
         int iters = 0;
         for (int i = 0; i < 60; i++) {
             iters++;
-            float e = DKstep(c0, c1, c2, c3, ro, rd, form);
+            real e = DKstep(c0, c1, c2, c3, ro, rd, form);
             e = gmax(e, DKstep(c1, c2, c3, c0, ro, rd, form));
             e = gmax(e, DKstep(c2, c3, c0, c1, ro, rd, form));
             e = gmax(e, DKstep(c3, c0, c1, c2, ro, rd, form));
             if (e < eps) break;
         }
         last_dk = iters;
+        dk_pix += (uint32_t)iters;
         if (st) { st->dk += iters; st->dk_hist[iters]++; }
         vec4 rs = { c0.x, c1.x, c2.x, c3.x };
-        vec4 ri = { fabsf(c0.y), fabsf(c1.y), fabsf(c2.y), fabsf(c3.y) };
+        vec4 ri = { r_abs(c0.y), r_abs(c1.y), r_abs(c2.y), r_abs(c3.y) };
         if (ri.x > eps || rs.x < 0.f) rs.x = 10000.f;
         if (ri.y > eps || rs.y < 0.f) rs.y = 10000.f;
         if (ri.z > eps || rs.z < 0.f) rs.z = 10000.f;
@@ -382,13 +395,13 @@ struct Frag {
         t = gmin(gmin(rs.x, rs.y), gmin(rs.z, rs.w));
         return t > 0 && t < 100 && t < tmin;
     }
-    vec3 getTorusNormal(vec3 ro, vec3 rd, float t, int num) {
+    vec3 getTorusNormal(vec3 ro, vec3 rd, real t, int num) {
         const rtb_torus& torus = S.toruses[num];
         vec4 q = v4(torus.quat_rotation);
         ro = rotate(q, ro - v3(torus.pos));
         rd = rotate(q, rd);
         vec3 pos = ro + rd * t;
-        float fy = torus.form[1], fx = torus.form[0];
+        real fy = torus.form[1], fx = torus.form[0];
         vec3 normal = pos * (vec3{ 1, 1, 1 } * (dot(pos, pos) - fy * fy) - fx * fx * vec3{ 1.0f, 1.0f, -1.0f });
         return normalize(rotate(quat_inv(q), normal));
     }
@@ -397,46 +410,46 @@ struct Frag {
     static bool isBetween(vec3 value, vec3 mn, vec3 mx) {        /* rt.frag:280-283 */
         return (value.x > mn.x && value.y > mn.y && value.z > mn.z) && (value.x < mx.x && value.y < mx.y && value.z < mx.z);
     }
-    static bool checkSurfaceEdges(vec3 o, vec3 d, float& tMin, float& tMax, vec3 v_min, vec3 v_max, float epsilon) {
+    static bool checkSurfaceEdges(vec3 o, vec3 d, real& tMin, real& tMax, vec3 v_min, vec3 v_max, real epsilon) {
         vec3 pt = d * tMin + o;
         if (!isBetween(pt, v_min, v_max)) {
             if (tMax < epsilon) return false;
             pt = d * tMax + o;
             if (!isBetween(pt, v_min, v_max)) return false;
-            float tmp = tMin; tMin = tMax; tMax = tmp;
+            real tmp = tMin; tMin = tMax; tMax = tmp;
         }
         return true;
     }
-    bool intersectSurface(vec3 ro, vec3 rd, int num, float tmin, float& t) {
+    bool intersectSurface(vec3 ro, vec3 rd, int num, real tmin, real& t) {
         vec3 orig_ro = ro;
         vec3 orig_rd = rd;
         const rtb_surface& surface = S.surfaces[num];
         vec4 q = v4(surface.quat_rotation);
         ro = rotate(q, ro - v3(surface.pos));
         rd = rotate(q, rd);
-        float a = surface.a, b = surface.b, c = surface.c, d = surface.d, e = surface.e, f = surface.f;
-        float d1 = rd.x, d2 = rd.y, d3 = rd.z;
-        float o1 = ro.x, o2 = ro.y, o3 = ro.z;
-        float p1 = 2 * a * d1 * o1 + 2 * b * d2 * o2 + 2 * c * d3 * o3 + d * d3 + d2 * e;
-        float p2 = a * d1 * d1 + b * d2 * d2 + c * d3 * d3;
-        float p3 = a * o1 * o1 + b * o2 * o2 + c * o3 * o3 + d * o3 + e * o2 + f;
-        float p4 = sqrtf(p1 * p1 - 4 * p2 * p3);
-        if (fabsf(p2) < 1e-6f) {                 /* quirk Q2: accepts t GREATER than tmin, rt.frag:541-545 */
+        real a = surface.a, b = surface.b, c = surface.c, d = surface.d, e = surface.e, f = surface.f;
+        real d1 = rd.x, d2 = rd.y, d3 = rd.z;
+        real o1 = ro.x, o2 = ro.y, o3 = ro.z;
+        real p1 = 2 * a * d1 * o1 + 2 * b * d2 * o2 + 2 * c * d3 * o3 + d * d3 + d2 * e;
+        real p2 = a * d1 * d1 + b * d2 * d2 + c * d3 * d3;
+        real p3 = a * o1 * o1 + b * o2 * o2 + c * o3 * o3 + d * o3 + e * o2 + f;
+        real p4 = r_sqrt(p1 * p1 - 4 * p2 * p3);
+        if (r_abs(p2) < 1e-6f) {                 /* quirk Q2: accepts t GREATER than tmin, rt.frag:541-545 */
             t = -p3 / p1;
             return t > tmin;
         }
-        float mn = FLT_MAX;
-        float mx = FLT_MAX;
-        float t1 = (-p1 - p4) / (2 * p2);
-        float t2 = (-p1 + p4) / (2 * p2);
-        float epsilon = 1e-4f;
+        real mn = FLT_MAX;
+        real mx = FLT_MAX;
+        real t1 = (-p1 - p4) / (2 * p2);
+        real t2 = (-p1 + p4) / (2 * p2);
+        real epsilon = 1e-4f;
         if (t1 > epsilon && t1 < mn) { mn = t1; mx = t2; }
         if (t2 > epsilon && t2 < mn) { mn = t2; mx = t1; }
         if (!checkSurfaceEdges(orig_ro, orig_rd, mn, mx, v3(surface.v_min), v3(surface.v_max), epsilon)) return false;
         t = mn;
         return t < tmin;
     }
-    vec3 getSurfaceNormal(vec3 ro, vec3 rd, float t, int num) {
+    vec3 getSurfaceNormal(vec3 ro, vec3 rd, real t, int num) {
         const rtb_surface& surface = S.surfaces[num];
         vec4 q = v4(surface.quat_rotation);
         ro = ro - v3(surface.pos);
@@ -449,10 +462,10 @@ struct Frag {
     }
 
     /* rt.frag:587-628 */
-    float calcInter(vec3 ro, vec3 rd, int& num, int& type) {
+    real calcInter(vec3 ro, vec3 rd, int& num, int& type) {
         if (st) st->rays_nearest++;
-        float tmin = maxDist;
-        float t;
+        real tmin = maxDist;
+        real t;
         const rtb_defines& D = S.def;
         if (st) { st->tests[RTB_TYPE_PLANE] += D.plane_size; st->tests[RTB_TYPE_SPHERE] += D.sphere_size;
                   st->tests[RTB_TYPE_SURFACE] += D.surface_size; st->tests[RTB_TYPE_BOX] += D.box_size;
@@ -472,18 +485,19 @@ struct Frag {
             if (intersectRing(ro, rd, i, tmin, t)) { num = i; tmin = t; type = RTB_TYPE_RING; }
         for (int i = 0; i < D.light_point_size; i++)
             if (intersectSphere(ro, rd, v4(S.lights_point[i].pos), false, tmin, t)) { num = i; tmin = t; type = RTB_TYPE_POINT_LIGHT; }
+        path_mix(tmin < maxDist ? (uint32_t)((type << 24) | (num & 0xffffff)) : 0xffffffffu);
         return tmin;
     }
 
     /* rt.frag:630-658 (PLANE_ONESIDE == 1: planes never shadow; no early exit) */
-    float inShadow(vec3 ro, vec3 rd, float dist) {
+    real inShadow(vec3 ro, vec3 rd, real dist) {
         if (st) st->rays_shadow++;
         const rtb_defines& D = S.def;
         if (st) { st->tests[RTB_TYPE_SPHERE] += D.sphere_size; st->tests[RTB_TYPE_SURFACE] += D.surface_size;
                   st->tests[RTB_TYPE_BOX] += D.box_size; st->tests[RTB_TYPE_TORUS] += D.torus_size;
                   st->tests[RTB_TYPE_RING] += D.ring_size; }
-        float t;
-        float shadow = 0;
+        real t;
+        real shadow = 0;
         for (int i = 0; i < D.sphere_size; i++)
             if (intersectSphere(ro, rd, v4(S.spheres[i].obj), false, dist, t)) shadow = 1;
         for (int i = 0; i < D.surface_size; i++)
@@ -503,32 +517,33 @@ struct Frag {
                     shadow = 1;
                 }
             }
+        path_mix(shadow > 0 ? 0x5ad0u : 0x11e7u);
         return gmin(shadow, 1);
     }
 
     /* rt.frag:660-679 */
-    void calcShade2(vec3 light_dir, vec3 light_color, float intensity, vec3 pt, vec3 rd, const Material& material, vec3 normal,
-                    bool doShadow, float dist, float distDiv, vec3& diffuse, vec3& specular) {
+    void calcShade2(vec3 light_dir, vec3 light_color, real intensity, vec3 pt, vec3 rd, const Material& material, vec3 normal,
+                    bool doShadow, real dist, real distDiv, vec3& diffuse, vec3& specular) {
         if (st) st->light_evals++;
         light_dir = normalize(light_dir);
-        float dp = clampf(dot(normal, light_dir), 0.0f, 1.0f);
+        real dp = clampf(dot(normal, light_dir), 0.0f, 1.0f);
         light_color *= dp;
         if (doShadow) {                                         /* SHADOW_ENABLED 1, rt.frag:15 */
-            float sh = 1 - inShadow(pt, light_dir, dist);
+            real sh = 1 - inShadow(pt, light_dir, dist);
             vec3 shadow = { sh, sh, sh };
             light_color *= vmax(shadow, S.SHADOW_AMBIENT);
         }
         diffuse += light_color * material.color * material.diffuse * intensity / distDiv;
         if (material.specular > 0) {
             vec3 reflection = reflect(light_dir, normal);
-            float specDp = clampf(dot(rd, reflection), 0.0f, 1.0f);
-            specular += light_color * powf(specDp, (float)material.specular) * intensity / distDiv;
+            real specDp = clampf(dot(rd, reflection), 0.0f, 1.0f);
+            specular += light_color * r_pow(specDp, (real)material.specular) * intensity / distDiv;
         }
     }
 
     /* rt.frag:681-709 */
     vec3 calcShade(vec3 pt, vec3 rd, const Material& material, vec3 normal, bool doShadow) {
-        float dist, distDiv;
+        real dist, distDiv;
         vec3 light_color, light_dir;
         vec3 diffuse = { 0, 0, 0 };
         vec3 specular = { 0, 0, 0 };
@@ -556,29 +571,29 @@ struct Frag {
     }
 
     /* rt.frag:711-715 */
-    static float getFresnel(vec3 normal, vec3 rd, float reflection) {
-        float ndotv = clampf(dot(normal, -rd), 0.0f, 1.0f);
-        return reflection + (1.0f - reflection) * powf(1.0f - ndotv, 5.0f);
+    static real getFresnel(vec3 normal, vec3 rd, real reflection) {
+        real ndotv = clampf(dot(normal, -rd), 0.0f, 1.0f);
+        return reflection + (1.0f - reflection) * r_pow(1.0f - ndotv, (real)5.0f);
     }
     /* rt.frag:717-742, DO_FRESNEL 1 */
-    static float FresnelReflectAmount(float n1, float n2, vec3 normal, vec3 incident, float refl) {
-        float r0 = (n1 - n2) / (n1 + n2);
+    static real FresnelReflectAmount(real n1, real n2, vec3 normal, vec3 incident, real refl) {
+        real r0 = (n1 - n2) / (n1 + n2);
         r0 *= r0;
-        float cosX = -dot(normal, incident);
+        real cosX = -dot(normal, incident);
         if (n1 > n2) {
-            float n = n1 / n2;
-            float sinT2 = n * n * (1.0f - cosX * cosX);
+            real n = n1 / n2;
+            real sinT2 = n * n * (1.0f - cosX * cosX);
             if (sinT2 > 1.0f) return 1.0f;
-            cosX = sqrtf(1.0f - sinT2);
+            cosX = r_sqrt(1.0f - sinT2);
         }
-        float x = 1.0f - cosX;
-        float ret = r0 + (1.0f - r0) * x * x * x * x * x;
+        real x = 1.0f - cosX;
+        real ret = r0 + (1.0f - r0) * x * x * x * x * x;
         ret = (refl + (1.0f - refl) * ret);
         return ret;
     }
 
     /* rt.frag:744-784 */
-    HitRecord get_hit_info(vec3 ro, vec3 rd, vec3 pt, float t, int num, int type) {
+    HitRecord get_hit_info(vec3 ro, vec3 rd, vec3 pt, real t, int num, int type) {
         HitRecord hr = {};
         if (st && type >= 0 && type < 7) st->shaded[type]++;
         if (type == RTB_TYPE_SPHERE) {
@@ -607,7 +622,7 @@ struct Frag {
                 hr.alpha = texColor.w;
             }
         }
-        float distance = length(pt - ro);
+        real distance = length(pt - ro);
         hr.bias_mult = (9e-3f * distance + 35) / 35e3f;
         return hr;
     }
@@ -617,7 +632,7 @@ struct Frag {
         vec3 color = { 0, 0, 0 };
         vec3 pt;
         int num = 0, type = 0;                                  /* pin Q1 */
-        float t = calcInter(ro, rd, num, type);
+        real t = calcInter(ro, rd, num, type);
         if (type == RTB_TYPE_POINT_LIGHT) return v3(S.lights_point[num].color);
         HitRecord hr;
         if (t < maxDist) {
@@ -631,14 +646,14 @@ struct Frag {
 
     /* rt.frag:804-902 */
     vec4 main_() {
-        float reflectMultiplier, refractMultiplier, tm;
+        real reflectMultiplier, refractMultiplier, tm;
         Material mat;
         vec3 pt, n;
         vec3 mask = { 1.0f, 1.0f, 1.0f };
         vec3 color = { 0.0f, 0.0f, 0.0f };
         vec3 ro = v3(S.scene.camera_pos);
         vec3 rd = getRayDir();
-        float absorbDistance = 0.0f;
+        real absorbDistance = 0.0f;
         int type = 0;
         int num = 0;
         HitRecord hr;
@@ -696,7 +711,7 @@ struct Frag {
                     }
                 }
             } else {
-                glsim::rgba c = glsim::texture_cube(S.skybox, rd.x, rd.y, rd.z);
+                glsim::rgba c = glsim::texture_cube(S.skybox, to_f(rd.x), to_f(rd.y), to_f(rd.z));
                 color += vec3{ c.r, c.g, c.b } * mask;
                 break;
             }
@@ -716,10 +731,14 @@ void add_stats(orc_stats* dst, const Stats& s, uint64_t pixels) {
     for (int i = 0; i <= 60; i++) dst->dk_hist[i] += s.dk_hist[i];
 }
 
+/* what the *_ex entry points report per pixel besides the colour */
+struct PixelInfo { uint64_t path; uint32_t dk; };
+
 /* Run the four invocations of one 2x2 quad to the derivative fixed point (pin Q9). */
-void render_quad(const Scene& S, int qx, int qy, float* out4x4, Stats* stats) {
+void render_quad(const Scene& S, int qx, int qy, float* out4x4, Stats* stats, PixelInfo* info4 = nullptr) {
     QuadCtx quad;
     vec4 col[4];
+    PixelInfo info[4] = {};
     Stats last;
     for (int pass = 0; pass < 8; pass++) {
         Stats local;
@@ -730,6 +749,7 @@ void render_quad(const Scene& S, int qx, int qy, float* out4x4, Stats* stats) {
             f.fragx = (float)(qx + (l & 1)) + 0.5f;
             f.fragy = (float)(qy + (l >> 1)) + 0.5f;
             col[l] = f.main_();
+            info[l] = { f.path, f.dk_pix };
         }
         last = local;
         bool any = false, same = true;
@@ -751,7 +771,10 @@ void render_quad(const Scene& S, int qx, int qy, float* out4x4, Stats* stats) {
         for (int i = 0; i < 7; i++) { stats->tests[i] += last.tests[i]; stats->shaded[i] += last.shaded[i]; }
         for (int i = 0; i <= 60; i++) stats->dk_hist[i] += last.dk_hist[i];
     }
-    for (int l = 0; l < 4; l++) { out4x4[l * 4 + 0] = col[l].x; out4x4[l * 4 + 1] = col[l].y; out4x4[l * 4 + 2] = col[l].z; out4x4[l * 4 + 3] = col[l].w; }
+    for (int l = 0; l < 4; l++) {
+        out4x4[l * 4 + 0] = to_f(col[l].x); out4x4[l * 4 + 1] = to_f(col[l].y); out4x4[l * 4 + 2] = to_f(col[l].z); out4x4[l * 4 + 3] = to_f(col[l].w);
+        if (info4) info4[l] = info[l];
+    }
 }
 
 int resolve_threads(int n) {
@@ -760,15 +783,15 @@ int resolve_threads(int n) {
     return hc ? (int)hc : 1;
 }
 
-}  // namespace
+struct Handle { Scene S; };
 
-struct orc_handle { Scene S; };
+}  // namespace
 
 extern "C" {
 
-orc_handle* orc_create(const orc_scene_desc* d) {
+orc_handle* ORC_API(create)(const orc_scene_desc* d) {
     if (!d || !d->scene) return nullptr;
-    orc_handle* h = new orc_handle();
+    Handle* h = new Handle();
     Scene& S = h->S;
     S.def = d->defines;
     S.scene = *d->scene;
@@ -792,14 +815,18 @@ orc_handle* orc_create(const orc_scene_desc* d) {
     }
     for (int u = 1; u <= 5; u++)
         if (d->tex2d[u].px) glsim::build_mips(S.tex[u], d->tex2d[u].px, d->tex2d[u].w, d->tex2d[u].h, d->tex2d[u].ch);
-    return h;
+    return (orc_handle*)h;
 }
 
-void orc_destroy(orc_handle* h) { delete h; }
-void orc_set_pairing(orc_handle* h, int rule) { h->S.pairing = rule; }
+void ORC_API(destroy)(orc_handle* h) { delete (Handle*)h; }
+void ORC_API(set_pairing)(orc_handle* h, int rule) { ((Handle*)h)->S.pairing = rule; }
 
-int orc_render_quads(orc_handle* h, int n, const int32_t* qx, const int32_t* qy, float* out, orc_stats* stats, int n_threads) {
+/* n 2x2 quads; besides the colours, per pixel: path[n][4] (hash of the discrete path) and dk[n][4] (Durand-Kerner trips); either may be NULL */
+int ORC_API(render_quads_ex)(orc_handle* hh, int n, const int32_t* qx, const int32_t* qy, float* out, uint64_t* path, uint32_t* dk,
+                             uint32_t sample, orc_stats* stats, int n_threads) {
+    Handle* h = (Handle*)hh;
     if (!h || n < 0) return -1;
+    orc_real::sr_set_sample(sample);                            /* selects the random-rounding stream of the stochastic variant; unused by the others */
     int nt = resolve_threads(n_threads);
     if (nt > n) nt = n > 0 ? n : 1;
     std::atomic<int> next(0);
@@ -810,7 +837,14 @@ int orc_render_quads(orc_handle* h, int n, const int32_t* qx, const int32_t* qy,
             int b = next.fetch_add(chunk);
             if (b >= n) break;
             int e = b + chunk < n ? b + chunk : n;
-            for (int i = b; i < e; i++) render_quad(h->S, qx[i], qy[i], out + (size_t)i * 16, &tstats[tid]);
+            for (int i = b; i < e; i++) {
+                PixelInfo info[4];
+                render_quad(h->S, qx[i], qy[i], out + (size_t)i * 16, &tstats[tid], info);
+                for (int l = 0; l < 4; l++) {
+                    if (path) path[(size_t)i * 4 + l] = info[l].path;
+                    if (dk) dk[(size_t)i * 4 + l] = info[l].dk;
+                }
+            }
         }
     };
     std::vector<std::thread> th;
@@ -822,8 +856,16 @@ int orc_render_quads(orc_handle* h, int n, const int32_t* qx, const int32_t* qy,
     return 0;
 }
 
-int orc_render(orc_handle* h, int x0, int y0, int w, int hgt, float* out, orc_stats* stats, int n_threads) {
+int ORC_API(render_quads)(orc_handle* h, int n, const int32_t* qx, const int32_t* qy, float* out, orc_stats* stats, int n_threads) {
+    return ORC_API(render_quads_ex)(h, n, qx, qy, out, nullptr, nullptr, 0, stats, n_threads);
+}
+
+/* a window; path[hgt][w] and dk[hgt][w] as above */
+int ORC_API(render_ex)(orc_handle* hh, int x0, int y0, int w, int hgt, float* out, uint64_t* path, uint32_t* dk, uint32_t sample,
+                       orc_stats* stats, int n_threads) {
+    Handle* h = (Handle*)hh;
     if (!h || (x0 | y0 | w | hgt) & 1 || w <= 0 || hgt <= 0) return -1;
+    orc_real::sr_set_sample(sample);
     int nt = resolve_threads(n_threads);
     int qrows = hgt / 2, qcols = w / 2;
     std::atomic<int> next(0);
@@ -834,10 +876,13 @@ int orc_render(orc_handle* h, int x0, int y0, int w, int hgt, float* out, orc_st
             if (r >= qrows) break;
             for (int c = 0; c < qcols; c++) {
                 float px[16];
-                render_quad(h->S, x0 + 2 * c, y0 + 2 * r, px, &tstats[tid]);
+                PixelInfo info[4];
+                render_quad(h->S, x0 + 2 * c, y0 + 2 * r, px, &tstats[tid], info);
                 for (int l = 0; l < 4; l++) {
-                    size_t o = ((size_t)(2 * r + (l >> 1)) * w + (size_t)(2 * c + (l & 1))) * 4;
-                    memcpy(out + o, px + l * 4, 16);
+                    size_t p = (size_t)(2 * r + (l >> 1)) * w + (size_t)(2 * c + (l & 1));
+                    memcpy(out + p * 4, px + l * 4, 16);
+                    if (path) path[p] = info[l].path;
+                    if (dk) dk[p] = info[l].dk;
                 }
             }
         }
@@ -851,24 +896,28 @@ int orc_render(orc_handle* h, int x0, int y0, int w, int hgt, float* out, orc_st
     return 0;
 }
 
-float orc_calc_inter(orc_handle* h, const float ro[3], const float rd[3], int32_t* num, int32_t* type) {
-    Frag f(h->S, nullptr, nullptr);
+int ORC_API(render)(orc_handle* h, int x0, int y0, int w, int hgt, float* out, orc_stats* stats, int n_threads) {
+    return ORC_API(render_ex)(h, x0, y0, w, hgt, out, nullptr, nullptr, 0, stats, n_threads);
+}
+
+float ORC_API(calc_inter)(orc_handle* h, const float ro[3], const float rd[3], int32_t* num, int32_t* type) {
+    Frag f(((Handle*)h)->S, nullptr, nullptr);
     int n = *num, t = *type;
-    float tm = f.calcInter(v3(ro), v3(rd), n, t);
+    real tm = f.calcInter(v3(ro), v3(rd), n, t);
     *num = n; *type = t;
-    return tm;
+    return to_f(tm);
 }
 
-float orc_in_shadow(orc_handle* h, const float ro[3], const float rd[3], float dist) {
-    Frag f(h->S, nullptr, nullptr);
-    return f.inShadow(v3(ro), v3(rd), dist);
+float ORC_API(in_shadow)(orc_handle* h, const float ro[3], const float rd[3], float dist) {
+    Frag f(((Handle*)h)->S, nullptr, nullptr);
+    return to_f(f.inShadow(v3(ro), v3(rd), dist));
 }
 
-int orc_intersect(orc_handle* h, int type, int index, const float ro_[3], const float rd_[3], float tmin, float* t, int32_t* dk_iters) {
-    Frag f(h->S, nullptr, nullptr);
-    const Scene& S = h->S;
+int ORC_API(intersect)(orc_handle* h, int type, int index, const float ro_[3], const float rd_[3], float tmin, float* t, int32_t* dk_iters) {
+    const Scene& S = ((Handle*)h)->S;
+    Frag f(S, nullptr, nullptr);
     vec3 ro = v3(ro_), rd = v3(rd_);
-    float tt = 0.0f;
+    real tt = 0.0f;
     bool hit = false;
     switch (type) {
         case RTB_TYPE_SPHERE: hit = f.intersectSphere(ro, rd, v4(S.spheres[index].obj), S.spheres[index].hollow != 0, tmin, tt); break;
@@ -880,33 +929,35 @@ int orc_intersect(orc_handle* h, int type, int index, const float ro_[3], const 
         case RTB_TYPE_POINT_LIGHT: hit = f.intersectSphere(ro, rd, v4(S.lights_point[index].pos), false, tmin, tt); break;
         default: return -1;
     }
-    if (t) *t = tt;
+    if (t) *t = to_f(tt);
     if (dk_iters) *dk_iters = f.last_dk;
     return hit ? 1 : 0;
 }
 
-void orc_ray_dir(orc_handle* h, int x, int y, float out[3]) {
-    Frag f(h->S, nullptr, nullptr);
+void ORC_API(ray_dir)(orc_handle* h, int x, int y, float out[3]) {
+    Frag f(((Handle*)h)->S, nullptr, nullptr);
     f.fragx = (float)x + 0.5f; f.fragy = (float)y + 0.5f;
     vec3 d = f.getRayDir();
-    out[0] = d.x; out[1] = d.y; out[2] = d.z;
+    out[0] = to_f(d.x); out[1] = to_f(d.y); out[2] = to_f(d.z);
 }
 
+#if ORC_VARIANT == 0    /* the sampler model is fp32 in every variant: probed once */
 void orc_sample_cube(orc_handle* h, const float dir[3], float out[4]) {
-    glsim::rgba c = glsim::texture_cube(h->S.skybox, dir[0], dir[1], dir[2]);
+    glsim::rgba c = glsim::texture_cube(((Handle*)h)->S.skybox, dir[0], dir[1], dir[2]);
     out[0] = c.r; out[1] = c.g; out[2] = c.b; out[3] = c.a;
 }
 
 void orc_sample_2d(orc_handle* h, int unit, float u, float v, float lod, float out[4]) {
-    glsim::rgba c = glsim::texture_lod(h->S.tex[unit], u, v, lod);
+    glsim::rgba c = glsim::texture_lod(((Handle*)h)->S.tex[unit], u, v, lod);
     out[0] = c.r; out[1] = c.g; out[2] = c.b; out[3] = c.a;
 }
 
-int orc_mip_levels(orc_handle* h, int unit) { return (int)h->S.tex[unit].levels.size(); }
+int orc_mip_levels(orc_handle* h, int unit) { return (int)((Handle*)h)->S.tex[unit].levels.size(); }
 const uint8_t* orc_mip_level(orc_handle* h, int unit, int level, int32_t* w, int32_t* hgt) {
-    const glsim::Level& L = h->S.tex[unit].levels[level];
+    const glsim::Level& L = ((Handle*)h)->S.tex[unit].levels[level];
     *w = L.w; *hgt = L.h;
     return L.px.data();
 }
+#endif
 
 }  // extern "C"

@@ -213,16 +213,26 @@ __global__ void __launch_bounds__(QUAD_THREADS) quad_kernel(const __grid_constan
 }
 
 /* ------------------------------------------------------------------ pack kernel */
-/* raw std140 arrays -> hot geometry block (layout in rt_params.h).  One small block; exact copies
- * plus the squares r*r / R*R (single multiplies the shader would redo per test). */
+/* raw std140 arrays -> hot geometry block (layout in rt_params.h).  One small block.  Strict build: exact copies plus the
+ * squares r*r / R*R (single multiplies the shader would redo per test).  Fused build: the rotated primitives carry the 3x3
+ * matrix of their quaternion sandwich (computed in fp64, rounded once) and a few folded constants. */
+#if !RTB_STRICT
+/* rotate(q, v) = q (v, 0) q* (rt.frag:305-311) as a matrix; no normalisation, exactly like the shader */
+DEV void quat_matrix(const float* q, float* m) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    m[0] = (float)(w * w + x * x - y * y - z * z); m[1] = (float)(2.0 * (x * y - w * z)); m[2] = (float)(2.0 * (x * z + w * y));
+    m[3] = (float)(2.0 * (x * y + w * z)); m[4] = (float)(w * w - x * x + y * y - z * z); m[5] = (float)(2.0 * (y * z - w * x));
+    m[6] = (float)(2.0 * (x * z - w * y)); m[7] = (float)(2.0 * (y * z + w * x)); m[8] = (float)(w * w - x * x - y * y + z * z);
+}
+#endif
 __global__ void pack_kernel(const FrameParams P, uint8_t* dst) {
     const int tid = threadIdx.x, nt = blockDim.x;
     PPlane* planes = (PPlane*)(dst + P.lay.off_plane);
     PSphere* spheres = (PSphere*)(dst + P.lay.off_sphere);
-    PSurf* surfs = (PSurf*)(dst + P.lay.off_surf);
-    PBox* boxes = (PBox*)(dst + P.lay.off_box);
-    PTorus* tori = (PTorus*)(dst + P.lay.off_torus);
-    PRing* rings = (PRing*)(dst + P.lay.off_ring);
+    HSurf* surfs = (HSurf*)(dst + P.lay.off_surf);
+    HBox* boxes = (HBox*)(dst + P.lay.off_box);
+    HTorus* tori = (HTorus*)(dst + P.lay.off_torus);
+    HRing* rings = (HRing*)(dst + P.lay.off_ring);
     PLight* lights = (PLight*)(dst + P.lay.off_light);
     for (int i = tid; i < P.n_plane; i += nt) {
         const rtb_plane& s = P.planes[i];
@@ -235,6 +245,12 @@ __global__ void pack_kernel(const FrameParams P, uint8_t* dst) {
         PSphere p = { s.obj[0], s.obj[1], s.obj[2], s.hollow != 0 ? __int_as_float(__float_as_int(r2) | 0x80000000) : r2 };
         spheres[i] = p;
     }
+    for (int i = tid; i < P.n_lpoint; i += nt) {
+        const rtb_light_point& s = P.lights_point[i];
+        PLight p = { s.pos[0], s.pos[1], s.pos[2], s.pos[3] * s.pos[3] };
+        lights[i] = p;
+    }
+#if RTB_STRICT
     for (int i = tid; i < P.n_surf; i += nt) {
         const rtb_surface& s = P.surfaces[i];
         PSurf p = { s.quat_rotation[0], s.quat_rotation[1], s.quat_rotation[2], s.quat_rotation[3], s.pos[0], s.pos[1], s.pos[2],
@@ -259,11 +275,39 @@ __global__ void pack_kernel(const FrameParams P, uint8_t* dst) {
                     s.r1, s.r2, s.textureNum, 0, 0 };
         rings[i] = p;
     }
-    for (int i = tid; i < P.n_lpoint; i += nt) {
-        const rtb_light_point& s = P.lights_point[i];
-        PLight p = { s.pos[0], s.pos[1], s.pos[2], s.pos[3] * s.pos[3] };
-        lights[i] = p;
+#else
+    for (int i = tid; i < P.n_surf; i += nt) {
+        const rtb_surface& s = P.surfaces[i];
+        PSurfM p;
+        quat_matrix(s.quat_rotation, p.m);
+        p.px = s.pos[0]; p.py = s.pos[1]; p.pz = s.pos[2];
+        p.a = s.a; p.b = s.b; p.c = s.c; p.d = s.d; p.e = s.e; p.f = s.f;
+        p.minx = s.v_min[0]; p.miny = s.v_min[1]; p.minz = s.v_min[2]; p.maxx = s.v_max[0]; p.maxy = s.v_max[1]; p.maxz = s.v_max[2];
+        surfs[i] = p;
     }
+    for (int i = tid; i < P.n_box; i += nt) {
+        const rtb_box& s = P.boxes[i];
+        PBoxM p;
+        quat_matrix(s.quat_rotation, p.m);
+        p.px = s.pos[0]; p.py = s.pos[1]; p.pz = s.pos[2]; p.fx = s.form[0]; p.fy = s.form[1]; p.fz = s.form[2]; p.tex = s.textureNum;
+        boxes[i] = p;
+    }
+    for (int i = tid; i < P.n_torus; i += nt) {
+        const rtb_torus& s = P.toruses[i];
+        PTorusM p;
+        quat_matrix(s.quat_rotation, p.m);
+        p.px = s.pos[0]; p.py = s.pos[1]; p.pz = s.pos[2];
+        p.R2 = s.form[0] * s.form[0]; p.r2 = s.form[1] * s.form[1]; p.k = p.R2 - p.r2; p.fourR2 = 4.f * p.R2;
+        tori[i] = p;
+    }
+    for (int i = tid; i < P.n_ring; i += nt) {
+        const rtb_ring& s = P.rings[i];
+        PRingM p;
+        quat_matrix(s.quat_rotation, p.m);
+        p.px = s.pos[0]; p.py = s.pos[1]; p.pz = s.pos[2]; p.r1 = s.r1; p.r2 = s.r2; p.tex = s.textureNum; p._0 = 0;
+        rings[i] = p;
+    }
+#endif
 }
 
 }  // namespace RTB_NS

@@ -25,6 +25,15 @@ struct PRing   { float qx, qy, qz, qw, px, py, pz, r1, r2; int32_t tex; int32_t 
 struct PSurf   { float qx, qy, qz, qw, px, py, pz, a, b, c, d, e, f, minx, miny, minz, maxx, maxy, maxz, _0; }; /* 80 B */
 struct PLight  { float x, y, z, r2; };                                       /* 16 B */
 
+/* The FUSED build (rtb_fast: FMA contraction, approximate reciprocals; parity by the envelope criterion) keeps
+ * every rotated primitive as the 3x3 matrix of its quaternion sandwich  rotate(q, v) = q (v,0) q*  (rt.frag:305-311;
+ * valid for non-unit q as well: the matrix carries |q|^2), row-major in m[9], followed by the position: the local ray
+ * is  rd' = M rd,  ro' = M (ro - p)  — 21 FMA-pipe instructions instead of the 94 of the two Hamilton products. */
+struct PBoxM   { float m[9], px, py, pz, fx, fy, fz; int32_t tex; };                          /* 64 B */
+struct PTorusM { float m[9], px, py, pz, R2, r2, k, fourR2; };                                /* 64 B; k = R2 - r2 */
+struct PRingM  { float m[9], px, py, pz, r1, r2; int32_t tex; int32_t _0; };                  /* 64 B */
+struct PSurfM  { float m[9], px, py, pz, a, b, c, d, e, f, minx, miny, minz, maxx, maxy, maxz; };  /* 96 B */
+
 /* byte offsets of each section inside the packed block (all multiples of 16) */
 struct PackedLayout {
     uint32_t off_plane, off_sphere, off_surf, off_box, off_torus, off_ring, off_light;

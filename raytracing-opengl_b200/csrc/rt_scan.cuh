@@ -46,10 +46,8 @@ DEV Derivs quad_derivs(bool site, int tag, vec2 uv) {
 /* TEX: 2-D textures may be referenced (quad kernel): textured rings add their alpha to
  * the shadow term (rt.frag:644-651) and need the quad exchange -> scan_scene must then be
  * called from warp-uniform control flow.  ctx = 0 main path / 1 getReflectedColor.
- * GATE: lanes with active == false skip the tests (quad kernel: dead paths and helper lanes are common).
- * The persistent kernel passes RTB_PERSIST_GATE (default true: measured faster when it was introduced, before the cooperative
- * drain existed).  With the cooperative drain idle lanes exist only in the last trips of a frame; GATE = false would let them
- * re-scan their last ray (result dropped) and save the 4-instruction branch region per test: an A/B candidate, DESIGN.md section 8. */
+ * GATE: lanes with active == false skip the tests (quad kernel: dead paths and helper lanes are common; persistent kernel: see
+ * RTB_PERSIST_GATE in rt_persistent.cuh). */
 template <bool COUNT, bool TEX, bool GATE>
 DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, bool active, bool shadow_mode, float limit, int ctx,
                     float& tmin_out, int& id_out, float& shadow_out, vec2& ring_uv_out, Counters& cnt) {
@@ -126,7 +124,7 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
     for (int i = 0; i < P.n_ring; i++) {
         vec2 uv = mk2(0.f, 0.f);
         bool hit = on && intersectRing(K, ro, rd, S.rings + i, tmin, t, uv);
-        int tex = ldsi(S.rings + i, offsetof(PRing, tex));
+        int tex = ldsi(S.rings + i, offsetof(HRing, tex));
         if (hit && !shadow_mode) { tmin = t; id = make_id(RTB_TYPE_RING, i); ring_uv = uv; }
         if (TEX && tex > 0) {
             bool site = hit && shadow_mode;

@@ -152,15 +152,16 @@ bool scene_uses_textures(const rtb_ctx* c) {
     return false;
 }
 
-PackedLayout make_layout(const rtb_defines& d) {
+/* the strict build stages quaternion records, the fused build matrix records (rt_params.h) */
+PackedLayout make_layout(const rtb_defines& d, bool strict) {
     PackedLayout L;
     uint32_t o = 0;
     L.off_plane = o;  o += align16(d.plane_size * sizeof(PPlane));
     L.off_sphere = o; o += align16(d.sphere_size * sizeof(PSphere));
-    L.off_surf = o;   o += align16(d.surface_size * sizeof(PSurf));
-    L.off_box = o;    o += align16(d.box_size * sizeof(PBox));
-    L.off_torus = o;  o += align16(d.torus_size * sizeof(PTorus));
-    L.off_ring = o;   o += align16(d.ring_size * sizeof(PRing));
+    L.off_surf = o;   o += align16(d.surface_size * (strict ? sizeof(PSurf) : sizeof(PSurfM)));
+    L.off_box = o;    o += align16(d.box_size * (strict ? sizeof(PBox) : sizeof(PBoxM)));
+    L.off_torus = o;  o += align16(d.torus_size * (strict ? sizeof(PTorus) : sizeof(PTorusM)));
+    L.off_ring = o;   o += align16(d.ring_size * (strict ? sizeof(PRing) : sizeof(PRingM)));
     L.off_light = o;  o += align16(d.light_point_size * sizeof(PLight));
     L.total_bytes = o < 16 ? 16 : o;
     return L;
@@ -206,7 +207,8 @@ int do_render(rtb_ctx* ctx, float* target, cudaStream_t st, bool counted, bool t
     P.surfaces = (const rtb_surface*)ctx->raw[RTB_BIND_SURFACES]; P.boxes = (const rtb_box*)ctx->raw[RTB_BIND_BOXES];
     P.toruses = (const rtb_torus*)ctx->raw[RTB_BIND_TORUSES]; P.rings = (const rtb_ring*)ctx->raw[RTB_BIND_RINGS];
     P.lights_point = (const rtb_light_point*)ctx->raw[RTB_BIND_LIGHTS_POINT]; P.lights_direct = (const rtb_light_direct*)ctx->raw[RTB_BIND_LIGHTS_DIRECT];
-    P.lay = make_layout(d);
+    const bool strict = ctx->opt_strict != 0;
+    P.lay = make_layout(d, strict);
     if (P.lay.total_bytes > ctx->packed_cap) {
         if (ctx->packed) cudaFree(ctx->packed);
         ctx->packed_cap = P.lay.total_bytes + 4096;
@@ -228,7 +230,6 @@ int do_render(rtb_ctx* ctx, float* target, cudaStream_t st, bool counted, bool t
     P.counters = counted ? ctx->counters : nullptr;
     P.cta_times = nullptr;
 
-    const bool strict = ctx->opt_strict != 0;
     int kernel = ctx->opt_kernel;
     const bool textured = scene_uses_textures(ctx);
     if (kernel == RTB_KERNEL_AUTO) kernel = textured ? RTB_KERNEL_QUAD : RTB_KERNEL_PERSISTENT;
@@ -413,7 +414,7 @@ int rtb_set_texture2d(rtb_ctx* ctx, int unit, const uint8_t* pixels, int w, int 
 int rtb_set_option(rtb_ctx* ctx, const char* key, int value) {
     if (!ctx || !key) return fail(ctx, RTB_ERR_INVALID, "null argument");
     if (!strcmp(key, "kernel")) { if (value < 0 || value > 2) return fail(ctx, RTB_ERR_INVALID, "kernel must be 0..2"); ctx->opt_kernel = value; }
-    else if (!strcmp(key, "strict")) ctx->opt_strict = value ? 1 : 0;
+    else if (!strcmp(key, "strict")) { if ((value ? 1 : 0) != ctx->opt_strict) ctx->dirty = true; ctx->opt_strict = value ? 1 : 0; }   /* the two builds stage different records */
     else if (!strcmp(key, "cull")) ctx->opt_cull = value ? 1 : 0;
     else if (!strcmp(key, "ctas_per_sm")) ctx->opt_ctas_per_sm = value;
     else if (!strcmp(key, "coop")) ctx->opt_coop = value ? 1 : 0;

@@ -1,0 +1,136 @@
+"""The envelope criterion: parity of the FUSED CUDA build (FMA contraction, MUFU reciprocals, rotation matrices).
+
+The strict build reproduces the fp32 oracle on every pixel.  The fused build cannot: it evaluates the same algorithm with
+differently rounded operations, exactly what a second conformant GLSL implementation would do (GLSL 3.30 4.5.1 / 4.x 4.7.1:
+`a*b+c` may be contracted, division / sqrt / pow are accurate to a few ulp only).  Ulp-level differences are amplified by
+every reflection off a curved surface and by specular exponents up to 200, and they flip discrete decisions (which primitive
+is nearest, shadowed or not, Durand-Kerner trip counts), so for some pixels the shader's own arithmetic does not determine the
+colour to the 1e-4 tolerance at all.  The criterion separates those pixels from errors of the kernel:
+
+    ensemble   = the oracle restatement (same control flow, same inputs) evaluated
+                   - in fp64 (oracle/real_types.h, variant 1),
+                   - K1 times in fp32 with stochastic rounding (variant 2: every operation returns one of the two fp32
+                     neighbours of its exact result) — conformant arithmetic,
+                   - K2 times with EXAGGERATED rounding noise (+-AMP ulps per operation), used for the path test only.
+    spread(p)  = max over fp64 and the K1 conformant members of |member(p) - oracle32(p)|   (max over channels)
+    determined = spread(p) <= TOL/4  and every one of the 1 + K1 + K2 members takes the same discrete path as oracle32
+                 (hash of the hit-id sequence and the shadow outcomes)
+    a fused pixel PASSES when  |fused(p) - oracle32(p)| <= TOL  or  p is not determined.
+    AVOIDABLE OUTLIER = a determined pixel the fused build misses by more than TOL.  The tests demand zero.
+
+Why TOL/4 and why the exaggerated members: a finite ensemble must not blame a correct implementation.  A pixel with a
+continuous sensitivity sigma ~ TOL/2 would slip through a TOL/2 gate with probability ~1e-2 and then be missed by a correct
+implementation with probability ~5e-2; at TOL/4 both factors collapse.  A pixel that sits within an ulp of a discrete flip
+flips in any single conformant evaluation with a probability well below 1/2, so K1 = 4 members overlook it often; under
++-AMP-ulp noise the flip probability saturates near 1/2 per member and K2 = 8 members overlook it with probability 2^-8.
+The price is coverage: pixels whose path survives 1-ulp but not AMP-ulp noise are excluded although implementations agree on
+them.  Both fractions are reported (frac_within_tol is the raw agreement with oracle32, frac_undetermined the excluded part).
+
+Calibration: independent stochastic-rounding samples (not members of the ensemble) are conformant evaluations by construction,
+so their avoidable-outlier count measures how often the criterion blames a correct implementation
+(tests/golden/make_envelope.py prints it for every fixture; tests/test_envelope.py re-checks a window on the CPU).
+"""
+import hashlib
+import os
+
+import numpy as np
+
+TOL = 1e-4
+FIXTURES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "envelope")
+
+# name -> (BASELINE.json config, scale): the five configs at sizes the ensemble finishes in minutes, plus configs[0] at full size
+CASES = {
+    "default256": ("default256", 1.0),
+    "default1080": ("default1080", 1 / 8),
+    "spheres4k": ("spheres4k", 1 / 16),
+    "tori1080": ("tori1080", 1 / 10),
+    "mixed1024_4k": ("mixed1024_4k", 1 / 24),
+    "mixed1024_8k": ("mixed1024_8k", 1 / 48),
+}
+
+
+def scene_digest(sc) -> str:
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(sc.scene).tobytes())
+    for n in ("spheres", "planes", "surfaces", "boxes", "toruses", "rings", "lights_point", "lights_direct"):
+        h.update(sc.array(n).tobytes())
+    h.update(np.asarray(sc.ambient_color, dtype=np.float32).tobytes())
+    h.update(np.asarray(sc.shadow_ambient, dtype=np.float32).tobytes())
+    return h.hexdigest()
+
+
+def pix_err(a, b):
+    """max over channels of |a - b|; NaN in both = 0, NaN in one = inf"""
+    d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+    both = np.isnan(a) & np.isnan(b)
+    d = np.where(both, 0.0, np.where(np.isnan(d), np.inf, d))
+    return d.max(axis=-1)
+
+
+K1, K2, AMP = 4, 8, 16
+
+
+def ensemble(sc, ts, k1=K1, k2=K2, amp=AMP, quads=None, window=None, threads=0):
+    """(oracle32 image, spread, path_differs) over the whole canvas, a window (x0, y0, w, h), or the 2x2 quads (qx, qy)."""
+    from oracle.binding import Oracle
+
+    def run(prec, sample=0):
+        o = Oracle(sc, ts, precision=prec)
+        try:
+            if quads is not None:
+                return o.render_quads_ex(quads[0], quads[1], sample=sample, threads=threads)
+            if window is not None:
+                return o.render_ex(*window, sample=sample, threads=threads)
+            return o.render_ex(sample=sample, threads=threads)
+        finally:
+            o.close()
+
+    o32, p32, _ = run("f32")
+    spread = np.zeros(o32.shape[:-1], dtype=np.float64)
+    pathdiff = np.zeros(o32.shape[:-1], dtype=bool)
+    for img, path, _ in [run("f64")] + [run("sr", k) for k in range(k1)]:
+        spread = np.maximum(spread, pix_err(img, o32))
+        pathdiff |= path != p32
+    for k in range(k2):
+        _, path, _ = run("sr", (amp << 16) | (k1 + k))
+        pathdiff |= path != p32
+    return o32, spread, pathdiff
+
+
+def judge(img, o32, spread, pathdiff, tol=TOL):
+    """Statistics of one image under the envelope criterion."""
+    err = pix_err(img, o32)
+    determined = (spread <= tol / 4) & ~pathdiff
+    within = err <= tol
+    avoidable = determined & ~within
+    n = err.size
+    return {
+        "pixels": int(n),
+        "frac_within_tol": float(within.mean()),
+        "frac_undetermined": float((~determined).mean()),
+        "frac_pass": float((within | ~determined).mean()),
+        "avoidable_outliers": int(avoidable.sum()),
+        "worst_avoidable": float(err[avoidable].max()) if avoidable.any() else 0.0,
+        "max_err_determined": float(np.where(determined, err, 0.0).max()),
+    }
+
+
+def fixture_path(name):
+    return os.path.join(FIXTURES, name + ".npz")
+
+
+def save_fixture(name, sc, spread, pathdiff):
+    os.makedirs(FIXTURES, exist_ok=True)
+    h, w = spread.shape
+    np.savez_compressed(fixture_path(name), spread=np.minimum(spread, 6e4).astype(np.float16), pathdiff=np.packbits(pathdiff.ravel()),
+                        shape=np.array([h, w], dtype=np.int32), ensemble=np.array([K1, K2, AMP], dtype=np.int32), digest=np.array(scene_digest(sc)))
+
+
+def load_fixture(name):
+    """(config, scale, spread [h, w] float64, pathdiff [h, w] bool, scene digest)"""
+    z = np.load(fixture_path(name))
+    h, w = (int(x) for x in z["shape"])
+    spread = z["spread"].astype(np.float64).reshape(h, w)
+    pathdiff = np.unpackbits(z["pathdiff"])[: h * w].astype(bool).reshape(h, w)
+    cfg, scale = CASES[name]
+    return cfg, scale, spread, pathdiff, str(z["digest"])

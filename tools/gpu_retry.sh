@@ -1,0 +1,11 @@
+#!/bin/bash
+# Development: run one gpurun call, retrying while the pod answers "busy" (exit code 3: nothing charged).
+# usage: tools/gpu_retry.sh <log> <gpurun args...>
+log=$1; shift
+for i in $(seq 1 20); do
+  /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1
+  rc=$?
+  [ $rc -ne 3 ] && exit $rc
+  sleep 90
+done
+exit 3
