@@ -42,6 +42,12 @@ enum rtb_kernel {
     RTB_KERNEL_PERSISTENT = 2  /* persistent threads, per-lane ray refill (scenes without 2-D textures) */
 };
 
+/* How the scanline blocks of the ranks reach the root's frame (multi-GPU). */
+enum rtb_gather_mode {
+    RTB_GATHER_NCCL = 0,       /* one grouped ncclSend/ncclRecv fan-in per frame + one de-interleave pass on the root (default) */
+    RTB_GATHER_P2P = 1         /* single-process only: every rank's kernel stores its pixels straight into the root's frame over NVLink */
+};
+
 /* Per-frame work counters, filled by rtb_render_counted() (an instrumented,
  * untimed launch).  "ray" = one full-scene query: one calcInter (rt.frag:587)
  * or one inShadow (rt.frag:630) evaluation. */
@@ -67,9 +73,35 @@ rtb_ctx* rtb_create(int width, int height, int device);
 /* GLWrapper::~GLWrapper / stop()  (GLWrapper.h:19,29). */
 void rtb_destroy(rtb_ctx* ctx);
 
-/* Multi-GPU screen partition (no reference counterpart: the reference is single-GPU).
- * The frame is cut into blocks of `block_rows` scanlines; block b belongs to rank
- * b % world.  This context renders only its own blocks, packed in block order. */
+/* ---- multi-GPU (no reference counterpart: the reference is single-GPU) -------------------------------------
+ * The frame is cut into blocks of `block_rows` scanlines (a multiple of 4); block b belongs to rank b % world.
+ * A rank renders only its own blocks, packed in block order; every rank holds the whole scene.  Two ways to run it:
+ *
+ *  (1) ONE process, N devices — what a C++ host like the reference's main.cpp uses (host/GLWrapper.cpp: RT_GPUS=N):
+ *      rtb_create_multi() returns a context that behaves exactly like a single-device one; every entry point fans
+ *      out to the N devices, rtb_render() launches the N kernels and gathers the frame on device 0
+ *      (ncclCommInitAll; per frame one ncclGroupStart .. ncclSend/ncclRecv .. ncclGroupEnd and a de-interleave pass;
+ *      or, with option "gather" = RTB_GATHER_P2P, no collective at all: the kernels store into device 0's frame).
+ *  (2) one process PER device (torchrun, MPI): each process creates a single-device context, rank 0 calls
+ *      rtb_comm_unique_id() and ships the 128 bytes to the others by whatever the launcher offers, everyone calls
+ *      rtb_comm_init(); per frame rtb_render_to() + rtb_gather().
+ * NCCL is loaded at run time (dlopen libnccl.so.2) by the first of these calls; single-GPU use never needs it. */
+rtb_ctx* rtb_create_multi(int width, int height, int n_gpus, int block_rows);
+int rtb_n_gpus(const rtb_ctx* ctx);                    /* 1 for a single-device context */
+/* kernel time of every rank of the last rtb_render() and the device-side frame time on the root (launch of the first
+ * kernel to the end of the gather), both by CUDA events.  kernel_ms may be NULL; it holds rtb_n_gpus() values. */
+int rtb_rank_times(rtb_ctx* ctx, float* kernel_ms, float* frame_ms);
+
+#define RTB_COMM_ID_BYTES 128
+int rtb_comm_unique_id(uint8_t id[RTB_COMM_ID_BYTES]);
+/* joins the communicator and sets the partition (rank, world, block_rows) of this context */
+int rtb_comm_init(rtb_ctx* ctx, const uint8_t id[RTB_COMM_ID_BYTES], int rank, int world, int block_rows);
+/* Frame-end gather of mode (2): every rank passes its packed rows (device pointer; NULL = the context framebuffer), the
+ * root (rank 0) also the destination of the assembled frame (H*W*4 floats, device).  Ordered on `cuda_stream`
+ * (NULL = the context stream). */
+int rtb_gather(rtb_ctx* ctx, const void* local_rows_device, void* full_frame_device, void* cuda_stream);
+
+/* Lower level: the partition alone (a rank rendered on its own, tests). */
 int rtb_set_partition(rtb_ctx* ctx, int rank, int world, int block_rows);
 /* Number of scanlines this context owns under the current partition. */
 int rtb_local_rows(const rtb_ctx* ctx);
@@ -80,10 +112,18 @@ int rtb_local_rows(const rtb_ctx* ctx);
  * GLWrapper::to_string (GLWrapper.cpp:279-282). */
 int rtb_set_defines(rtb_ctx* ctx, const rtb_defines* defines);
 
-/* GLWrapper::init_buffer / update_buffer  (GLWrapper.h:37-38; GLWrapper.cpp:365-386).
+/* GLWrapper::init_buffer  (GLWrapper.h:37; GLWrapper.cpp:365-379: glBufferData).
  * `binding` is the uniform-block binding point of SceneManager.cpp:246-254
- * (enum rtb_binding).  bytes may be 0 and data NULL (SceneManager.cpp:246). */
+ * (enum rtb_binding).  Replaces the block: it now holds exactly `bytes` bytes.
+ * bytes may be 0 and data NULL (SceneManager.cpp:246); data NULL with bytes > 0
+ * allocates only.  The bytes are copied before the call returns (pinned staging
+ * inside the library; the device copy itself is asynchronous). */
 int rtb_upload(rtb_ctx* ctx, int binding, const void* data, size_t bytes);
+
+/* GLWrapper::update_buffer  (GLWrapper.h:38; GLWrapper.cpp:381-386: glBufferSubData(0, bytes)).
+ * Overwrites the first `bytes` bytes of the block and leaves the rest as it was;
+ * bytes beyond the block's size are an error (GL_INVALID_VALUE in the reference). */
+int rtb_update(rtb_ctx* ctx, int binding, const void* data, size_t bytes);
 
 /* GLWrapper::load_cubemap + set_skybox  (GLWrapper.h:27,35; GLWrapper.cpp:284-317).
  * Six decoded faces in GL order +X,-X,+Y,-Y,+Z,-Z, `channels` = 3 or 4 bytes per
@@ -96,11 +136,12 @@ int rtb_set_cubemap(rtb_ctx* ctx, const uint8_t* const faces[6], int w, int h, i
  * sampling is REPEAT + trilinear. */
 int rtb_set_texture2d(rtb_ctx* ctx, int unit, const uint8_t* pixels, int w, int h, int channels);
 
-/* Options: "kernel" (enum rtb_kernel), "strict" (1 = no FMA contraction, IEEE
- * div/sqrt: operation-for-operation the shader's arithmetic; 0 = fast build),
- * "cull" (1 = conservative bounding-sphere reject before the torus solve;
- * result-preserving, reported separately from the roofline), "ctas_per_sm" (quad kernel), "coop" (0 = switch the
- * persistent kernel's cooperative drain off: an A/B and test switch, results are identical). */
+/* Options: "kernel" (enum rtb_kernel); "strict" (1, the default = no FMA contraction, IEEE div/sqrt: operation for
+ * operation the shader's arithmetic, bit-comparable with the CPU oracle; 0 = the FUSED build: FMA contraction, MUFU
+ * reciprocals, rotation matrices — 1.6x faster, parity by the envelope criterion);
+ * "cull" (1 = conservative bounding-sphere reject before the torus solve; result-preserving, reported separately from
+ * the roofline); "ctas_per_sm" (quad kernel); "coop" (0 = switch the persistent kernel's cooperative drain off: an A/B
+ * and test switch, results are identical); "gather" (enum rtb_gather_mode, multi-GPU contexts). */
 int rtb_set_option(rtb_ctx* ctx, const char* key, int value);
 
 /* GLWrapper::draw()  (GLWrapper.h:34; GLWrapper.cpp:155-165): render one frame

@@ -15,6 +15,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_ORACLE = os.path.join(HERE, "liboracle.so")
 LIB_REF = os.path.join(HERE, "_ref", "libref.so")
+LIB_REF_FAST = os.path.join(HERE, "_ref", "libref_fast.so")          # timing copy (-O3 -march=x86-64-v3), bench.py only
+LIB_ORACLE_NATIVE = os.path.join(HERE, "liboracle_native.so")        # timing copy of the restatement, built on the timing box
 
 
 class _Image(C.Structure):
@@ -55,6 +57,18 @@ def have_ref() -> bool:
     return os.path.isfile(LIB_REF)
 
 
+def timing_flags(impl: str) -> str | None:
+    """Compiler flags of the timing copy of `impl` ('ref' / 'oracle'), building the restatement's copy on this box if needed; None = absent."""
+    if impl == "ref":
+        f = os.path.join(HERE, "_ref", "libref_fast.flags")
+        return open(f).read().strip() if os.path.isfile(LIB_REF_FAST) and os.path.isfile(f) else None
+    try:
+        subprocess.check_call(["make", "-C", HERE, "liboracle_native.so"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception:
+        return None
+    return "g++ -O3 -march=native -ffp-contract=off -fno-fast-math"
+
+
 def _make_desc(scene, textures, keep):
     """scene: SceneContainer; textures: TextureSet or None.  `keep` collects arrays that must outlive the call."""
     d = _Desc()
@@ -93,13 +107,16 @@ class Oracle:
     precision (restatement only, oracle/real_types.h): "f32" = the pinned fp32 restatement, "f64" = the same control flow in
     double, "sr" = fp32 with stochastic rounding (render_ex(sample=k) selects the k-th random-rounding stream)."""
 
-    def __init__(self, scene, textures=None, impl: str = "oracle", precision: str = "f32"):
+    def __init__(self, scene, textures=None, impl: str = "oracle", precision: str = "f32", timing_build: bool = False):
+        """timing_build: load the -O3 copy of the library (bench.py's CPU arm); results are the same bits, only faster."""
         self.impl = impl
         self.precision = precision
         if impl != "oracle" and precision != "f32":
             raise ValueError("oracle/_ref exists in fp32 only")
         self.p = PRECISIONS[precision] if impl == "oracle" else "ref"
         path = LIB_ORACLE if impl == "oracle" else LIB_REF
+        if timing_build:
+            path = LIB_ORACLE_NATIVE if impl == "oracle" else LIB_REF_FAST
         if not os.path.isfile(path):
             raise FileNotFoundError(f"{path} not built (make -C oracle{' ref' if impl == 'ref' else ''})")
         self.lib = C.CDLL(path)

@@ -173,6 +173,7 @@ struct Frag {
     uint64_t path = 1469598103934665603ull;
     uint32_t dk_pix = 0;
     void path_mix(uint32_t v) { path = (path ^ v) * 1099511628211ull; }
+    std::vector<float>* trace = nullptr;      /* debugging aid (orc*_trace): kind (0 calcInter / 1 inShadow), type, num, t or shadow */
 
     Frag(const Scene& s, Stats* stats, QuadCtx* q) : S(s), st(stats), quad(q) {}
 
@@ -486,6 +487,7 @@ struct Frag {
         for (int i = 0; i < D.light_point_size; i++)
             if (intersectSphere(ro, rd, v4(S.lights_point[i].pos), false, tmin, t)) { num = i; tmin = t; type = RTB_TYPE_POINT_LIGHT; }
         path_mix(tmin < maxDist ? (uint32_t)((type << 24) | (num & 0xffffff)) : 0xffffffffu);
+        if (trace) { trace->push_back(0.f); trace->push_back((float)type); trace->push_back((float)num); trace->push_back(to_f(tmin)); }
         return tmin;
     }
 
@@ -518,6 +520,7 @@ struct Frag {
                 }
             }
         path_mix(shadow > 0 ? 0x5ad0u : 0x11e7u);
+        if (trace) { trace->push_back(1.f); trace->push_back(0.f); trace->push_back(0.f); trace->push_back(to_f(shadow)); }
         return gmin(shadow, 1);
     }
 
@@ -932,6 +935,20 @@ int ORC_API(intersect)(orc_handle* h, int type, int index, const float ro_[3], c
     if (t) *t = to_f(tt);
     if (dk_iters) *dk_iters = f.last_dk;
     return hit ? 1 : 0;
+}
+
+/* debugging aid: the sequence of scene queries of pixel (x, y) — 4 floats per query (kind, type, num, t or shadow); returns the number of queries.
+ * (No derivative context: texture LODs are those of an isolated invocation.) */
+int ORC_API(trace)(orc_handle* h, int x, int y, uint32_t sample, float* out, int cap) {
+    orc_real::sr_set_sample(sample);
+    Frag f(((Handle*)h)->S, nullptr, nullptr);
+    std::vector<float> tr;
+    f.trace = &tr;
+    f.fragx = (float)x + 0.5f; f.fragy = (float)y + 0.5f;
+    f.main_();
+    int n = (int)tr.size() / 4;
+    for (int i = 0; i < n * 4 && i < cap * 4; i++) out[i] = tr[i];
+    return n;
 }
 
 void ORC_API(ray_dir)(orc_handle* h, int x, int y, float out[3]) {

@@ -11,5 +11,5 @@ alias module at the repository root.
   api       GLWrapper (src/GLWrapper.h) over the C-ABI of librtb200.so (CUDA, sm_100a; no CPU path)
 """
 from . import api, scene, scenes, textures  # noqa: F401
-from .api import GLWrapper, RtbError, gather_rows, measure_fp32_peak, setup_scene  # noqa: F401
+from .api import GLWrapper, RtbError, gather_rows, measure_fp32_peak, setup_scene, update_buffers  # noqa: F401
 from .scene import SceneContainer, SceneManager, SurfaceFactory  # noqa: F401

@@ -22,6 +22,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "librtb200.so")     # RTB200_LIB: development builds only
 
 KERNEL_AUTO, KERNEL_QUAD, KERNEL_PERSISTENT = 0, 1, 2
+GATHER_NCCL, GATHER_P2P = 0, 1
+COMM_ID_BYTES = 128
 
 
 class RtbError(RuntimeError):
@@ -65,6 +67,14 @@ def load_library() -> C.CDLL:
     L.rtb_local_rows.argtypes = [vp]
     L.rtb_set_defines.argtypes = [vp, vp]
     L.rtb_upload.argtypes = [vp, i, vp, sz]
+    L.rtb_update.argtypes = [vp, i, vp, sz]
+    L.rtb_create_multi.restype = vp
+    L.rtb_create_multi.argtypes = [i, i, i, i]
+    L.rtb_n_gpus.argtypes = [vp]
+    L.rtb_rank_times.argtypes = [vp, vp, C.POINTER(C.c_float)]
+    L.rtb_comm_unique_id.argtypes = [vp]
+    L.rtb_comm_init.argtypes = [vp, vp, i, i, i]
+    L.rtb_gather.argtypes = [vp, vp, vp, vp]
     L.rtb_set_cubemap.argtypes = [vp, C.POINTER(vp), i, i, i]
     L.rtb_set_texture2d.argtypes = [vp, i, vp, i, i, i]
     L.rtb_set_option.argtypes = [vp, C.c_char_p, i]
@@ -97,10 +107,13 @@ def measure_fp32_peak(device: int = 0) -> float:
 class GLWrapper:
     """src/GLWrapper.h, same method names; `draw()` launches the CUDA ray-trace pass."""
 
-    def __init__(self, width: int, height: int, fullScreen: bool = False, device: int = 0):
+    def __init__(self, width: int, height: int, fullScreen: bool = False, device: int = 0, n_gpus: int = 1, block_rows: int = 4):
+        """n_gpus > 1: ONE process drives devices 0..n_gpus-1 (rtb_create_multi); every method then fans out inside the
+        library and draw() ends with the frame gathered on device 0 (what the C++ host does under RT_GPUS=n)."""
         self._L = load_library()
         self.width, self.height = int(width), int(height)
         self.device = device
+        self.n_gpus, self.block_rows = int(n_gpus), int(block_rows)
         self._ctx = None
         self._ubos = {}                 # handle -> binding (update_buffer is static and only gets the handle)
         self._next_handle = 1
@@ -124,7 +137,10 @@ class GLWrapper:
 
     # -- GLWrapper.h:25  (GLWrapper.cpp:61-133: create context)
     def init_window(self) -> bool:
-        self._ctx = self._L.rtb_create(self.width, self.height, self.device)
+        if self.n_gpus > 1:
+            self._ctx = self._L.rtb_create_multi(self.width, self.height, self.n_gpus, self.block_rows)
+        else:
+            self._ctx = self._L.rtb_create(self.width, self.height, self.device)
         if not self._ctx:
             raise RtbError(self._L.rtb_last_error(None).decode())
         return True
@@ -172,16 +188,18 @@ class GLWrapper:
         handle = self._next_handle
         self._next_handle += 1
         self._ubos[handle] = bindingPoint
-        if data is None:
+        if data is None:                                                  # glBufferData(size, NULL): allocate, contents follow
             self._check(self._L.rtb_upload(self._ctx, bindingPoint, None, UBO_BLOCKS[name][1].itemsize if bindingPoint == 0 else 0))
         else:
-            self.update_buffer(handle, data)
+            a = np.ascontiguousarray(data)
+            self._check(self._L.rtb_upload(self._ctx, bindingPoint, a.ctypes.data if a.nbytes else None, a.nbytes))
         return handle
 
-    # -- GLWrapper.h:38  (GLWrapper.cpp:381-386)
+    # -- GLWrapper.h:38  (GLWrapper.cpp:381-386: glBufferSubData(0, size) — the block keeps its size)
     def update_buffer(self, ubo: int, data):
         a = np.ascontiguousarray(data)
-        self._check(self._L.rtb_upload(self._ctx, self._ubos[ubo], a.ctypes.data if a.nbytes else None, a.nbytes))
+        if a.nbytes:
+            self._check(self._L.rtb_update(self._ctx, self._ubos[ubo], a.ctypes.data, a.nbytes))
 
     # -- GLWrapper.h:34  (GLWrapper.cpp:155-165)
     def draw(self):
@@ -212,14 +230,17 @@ class GLWrapper:
     def sync(self):
         self._check(self._L.rtb_sync(self._ctx))
 
+    def _frame_rows(self) -> int:
+        return self.height if self.n_gpus > 1 else self.local_rows()
+
     def read_pixels(self) -> np.ndarray:
-        """RGBA32F [local_rows, W, 4]; row 0 = bottom scanline of this rank's first block."""
-        out = np.empty((self.local_rows(), self.width, 4), dtype=np.float32)
+        """RGBA32F [rows, W, 4], row 0 = bottom scanline: this rank's packed blocks, or the whole gathered frame of a multi-GPU context."""
+        out = np.empty((self._frame_rows(), self.width, 4), dtype=np.float32)
         self._check(self._L.rtb_read_rgba32f(self._ctx, out.ctypes.data))
         return out
 
     def read_pixels_u8(self) -> np.ndarray:
-        out = np.empty((self.local_rows(), self.width, 4), dtype=np.uint8)
+        out = np.empty((self._frame_rows(), self.width, 4), dtype=np.uint8)
         self._check(self._L.rtb_read_rgba8(self._ctx, out.ctypes.data))
         return out
 
@@ -240,6 +261,30 @@ class GLWrapper:
     def device_framebuffer(self) -> int:
         return self._L.rtb_device_framebuffer(self._ctx)
 
+    # ---- multi-GPU behind the C-ABI ----
+    def rank_times(self):
+        """(kernel ms of every rank, device-side frame ms incl. the gather) of the last draw()."""
+        k = (C.c_float * max(1, self._L.rtb_n_gpus(self._ctx)))()
+        f = C.c_float(0)
+        self._check(self._L.rtb_rank_times(self._ctx, k, C.byref(f)))
+        return [float(x) for x in k], float(f.value)
+
+    def comm_unique_id(self) -> bytes:
+        """rank 0 of a one-process-per-GPU job: the NCCL id the other ranks need (ship it with the launcher's own means)."""
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        rc = self._L.rtb_comm_unique_id(buf)
+        if rc != 0:
+            raise RtbError(self._L.rtb_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, comm_id: bytes, rank: int, world: int, block_rows: int = 4):
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(comm_id)
+        self._check(self._L.rtb_comm_init(self._ctx, buf, rank, world, block_rows))
+
+    def gather(self, local_ptr: int = 0, full_ptr: int = 0, stream: int = 0):
+        """the frame-end NCCL gather of a one-process-per-GPU job (rtb_gather): device pointers, ordered on `stream`"""
+        self._check(self._L.rtb_gather(self._ctx, local_ptr or None, full_ptr or None, stream or None))
+
 
 def setup_scene(gl: GLWrapper, scene, textures=None):
     """What main.cpp + SceneManager::init do with a scene_container: init_shaders, samplers, init_buffers
@@ -258,6 +303,18 @@ def setup_scene(gl: GLWrapper, scene, textures=None):
         handles[name] = gl.init_buffer(name, UBO_BLOCKS[name][0], scene.array(attr))
     gl.update_buffer(handles["scene_buf"], np.ascontiguousarray(scene.scene).reshape(1))
     return handles
+
+
+def update_buffers(gl: GLWrapper, scene, handles):
+    """SceneManager::update_buffers (SceneManager.cpp:266-276), what the frame loop calls every frame: the scene uniform and the
+    seven primitive / point-light arrays, empty ones skipped (:257-264).  lights_direct_buf is NOT among them: the reference
+    writes it once, in init_buffers (:254) — a host that re-sent it would change what an animated scene renders."""
+    gl.update_buffer(handles["scene_buf"], np.ascontiguousarray(scene.scene).reshape(1))
+    for name, attr in (("spheres_buf", "spheres"), ("planes_buf", "planes"), ("surfaces_buf", "surfaces"), ("boxes_buf", "boxes"),
+                       ("toruses_buf", "toruses"), ("rings_buf", "rings"), ("lights_point_buf", "lights_point")):
+        a = scene.array(attr)
+        if len(a):
+            gl.update_buffer(handles[name], a)
 
 
 def gather_rows(parts, height: int, world: int, block_rows: int = 16) -> np.ndarray:

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(QUAD_THREADS) quad_kernel(const __grid_constan
         }
         if (inside) {
             float4 o = make_float4(color.x, color.y, color.z, 1.0f);
-            *(float4*)(P.fb + ((size_t)ly * P.canvas_w + x) * 4) = o;
+            *(float4*)(P.fb + ((size_t)(P.fb_global ? y : ly) * P.canvas_w + x) * 4) = o;
         }
     }
     if (COUNT) flush_counters(P, cnt);

@@ -65,8 +65,9 @@ struct FrameParams {
     const uint8_t* packed; PackedLayout lay;
     /* samplers */
     CubeDesc cube; TexDesc tex[6];
-    /* output: this rank's scanlines, packed in block order (rtb_set_partition) */
-    float* fb; int32_t rank, world, block_rows, local_rows;
+    /* output: this rank's scanlines, packed in block order (rtb_set_partition) — or, fb_global != 0, the whole canvas (possibly
+     * the root GPU's frame reached over NVLink peer access), of which this rank writes its own scanlines at their final place */
+    float* fb; int32_t fb_global; int32_t rank, world, block_rows, local_rows;
     /* work distribution */
     unsigned int* tile_counter; int32_t n_tiles_x, n_tiles_y;
     /* options */

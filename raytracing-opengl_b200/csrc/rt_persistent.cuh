@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
                     int ly = ty * 4 + (qd >> 2) * 2 + ((l >> 1) & 1);
                     int y = global_row(P, ly);
                     if (x < P.canvas_w && ly < P.local_rows && y < P.canvas_h) {
-                        fb_off = ly * P.canvas_w + x;
+                        fb_off = (P.fb_global ? y : ly) * P.canvas_w + x;
                         mask = mk3(1.f, 1.f, 1.f); color = mk3(0.f, 0.f, 0.f);
                         ro = mk3(P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]);
                         rd = getRayDir(P, x, y);

@@ -14,43 +14,23 @@
 #include <vector>
 #include <algorithm>
 
-#include "../../include/rtb200.h"
-#include "rt_launch.h"
+#include "rtb_ctx.h"
 
 namespace {
-
 thread_local std::string g_last_error;
+}
 
-struct Tex2D { uint8_t* dev = nullptr; int w = 0, h = 0, levels = 0; uint32_t off[16] = { 0 }; };
-
-}  // namespace
-
-struct rtb_ctx {
-    int device = 0, n_sm = 0;
-    int width = 0, height = 0;
-    int rank = 0, world = 1, block_rows = 16, local_rows = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_upload = nullptr;
-    bool have_defines = false;
-    rtb_defines defines = {};
-    void* raw[RTB_NUM_BINDINGS] = { nullptr };
-    size_t raw_cap[RTB_NUM_BINDINGS] = { 0 }, raw_bytes[RTB_NUM_BINDINGS] = { 0 };
-    std::vector<uint8_t> shadow[RTB_NUM_BINDINGS];      /* host copies (scene uniform, textureNum inspection) */
-    uint8_t* packed = nullptr; size_t packed_cap = 0;
-    bool dirty = true;
-    unsigned int* tile_counter = nullptr;
-    unsigned long long* counters = nullptr;
-    unsigned long long* cta_times = nullptr;     /* RTB_DEBUG_TIMES=1: per-CTA start / drain / end stamps, printed by rtb_sync */
-    int cta_times_n = 0;
-    float* fb = nullptr; size_t fb_floats = 0;
-    uint8_t* fb8 = nullptr;                       /* RGBA8 copy of the frame, made on demand by rtb_read_rgba8 */
-    uint8_t* cube = nullptr; int cube_w = 0, cube_h = 0;
-    Tex2D tex[6];
-    int opt_kernel = RTB_KERNEL_AUTO, opt_strict = 0, opt_cull = 0, opt_ctas_per_sm = 0, opt_coop = 1;
-    rtb_stats stats = {};
-    bool timed_pending = false;
-    std::string err;
-};
+int rtb_fail(rtb_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (c) c->err = buf;
+    return code;
+}
+#define fail rtb_fail
 
 namespace {
 
@@ -68,29 +48,13 @@ __global__ void rgba8_kernel(const float4* __restrict__ src, uchar4* __restrict_
     dst[i] = make_uchar4(q(v.x), q(v.y), q(v.z), q(v.w));
 }
 
-int fail(rtb_ctx* c, int code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    g_last_error = buf;
-    if (c) c->err = buf;
-    return code;
-}
-
-#define CU(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) return fail(ctx, RTB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
-    } while (0)
-
 const size_t ELEM_SIZE[RTB_NUM_BINDINGS] = { sizeof(rtb_scene), sizeof(rtb_sphere), sizeof(rtb_plane), sizeof(rtb_surface), sizeof(rtb_box),
                                              sizeof(rtb_torus), sizeof(rtb_ring), sizeof(rtb_light_point), sizeof(rtb_light_direct) };
 
 uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
 
-int compute_local_rows(int height, int rank, int world, int block_rows) {
+}  // namespace
+int rtb_compute_local_rows(int height, int rank, int world, int block_rows) {
     int rows = 0;
     for (int b = rank; b * block_rows < height; b += world) {
         int r = height - b * block_rows;
@@ -98,6 +62,7 @@ int compute_local_rows(int height, int rank, int world, int block_rows) {
     }
     return rows;
 }
+namespace {
 
 /* GLWrapper::to_string (GLWrapper.cpp:279-282): the colour reaches the shader as the text "%f" */
 float round_through_percent_f(float v) {
@@ -107,7 +72,7 @@ float round_through_percent_f(float v) {
 }
 
 /* glGenerateMipmap stand-in: 2x2 box filter, floor(d/2) sizes, 8-bit round-half-up (DESIGN.md "samplers") */
-void build_mip_chain(const uint8_t* src, int w, int h, int ch, std::vector<uint8_t>& out, Tex2D& t) {
+void build_mip_chain(const uint8_t* src, int w, int h, int ch, std::vector<uint8_t>& out, RtbTex2D& t) {
     std::vector<uint8_t> cur((size_t)w * h * 4);
     for (size_t i = 0; i < (size_t)w * h; i++) {
         uint8_t r = src[i * ch], g = 0, b = 0, a = 255;
@@ -140,16 +105,45 @@ void build_mip_chain(const uint8_t* src, int w, int h, int ch, std::vector<uint8
     }
 }
 
-bool scene_uses_textures(const rtb_ctx* c) {
-    const rtb_defines& d = c->defines;
-    auto n_ok = [&](int binding, int n) { return c->shadow[binding].size() >= (size_t)n * ELEM_SIZE[binding]; };
-    if (n_ok(RTB_BIND_SPHERES, d.sphere_size))
-        for (int i = 0; i < d.sphere_size; i++) if (((const rtb_sphere*)c->shadow[RTB_BIND_SPHERES].data())[i].textureNum != 0) return true;
-    if (n_ok(RTB_BIND_BOXES, d.box_size))
-        for (int i = 0; i < d.box_size; i++) if (((const rtb_box*)c->shadow[RTB_BIND_BOXES].data())[i].textureNum != 0) return true;
-    if (n_ok(RTB_BIND_RINGS, d.ring_size))
-        for (int i = 0; i < d.ring_size; i++) if (((const rtb_ring*)c->shadow[RTB_BIND_RINGS].data())[i].textureNum != 0) return true;
+/* does an uploaded array reference a 2-D texture (textureNum != 0)?  Decided once per upload, on the caller's bytes */
+bool array_uses_textures(int binding, const void* data, size_t bytes) {
+    const size_t n = bytes / ELEM_SIZE[binding];
+    if (binding == RTB_BIND_SPHERES) { for (size_t i = 0; i < n; i++) if (((const rtb_sphere*)data)[i].textureNum != 0) return true; }
+    else if (binding == RTB_BIND_BOXES) { for (size_t i = 0; i < n; i++) if (((const rtb_box*)data)[i].textureNum != 0) return true; }
+    else if (binding == RTB_BIND_RINGS) { for (size_t i = 0; i < n; i++) if (((const rtb_ring*)data)[i].textureNum != 0) return true; }
     return false;
+}
+bool scene_uses_textures(const rtb_ctx* c) { return c->uses_tex[RTB_BIND_SPHERES] || c->uses_tex[RTB_BIND_BOXES] || c->uses_tex[RTB_BIND_RINGS]; }
+
+/* the current staging arena with room for `bytes` more (see RtbStageSlot in rtb_ctx.h) */
+int stage_reserve(rtb_ctx* ctx, size_t bytes, uint8_t** out) {
+    RtbStageSlot& s = ctx->stage[ctx->stage_cur];
+    if (s.pending) {                                  /* first use since this arena's frame was queued: its copies must be done (normally long ago) */
+        CU(cudaEventSynchronize(s.done));
+        s.pending = false;
+        s.used = 0;
+    }
+    const size_t need = s.used + ((bytes + 255) & ~(size_t)255);
+    if (need > s.cap) {
+        /* grow: copies already queued from the old arena must finish first (only while the scene is first being built) */
+        if (s.used) CU(cudaStreamSynchronize(ctx->stream));
+        if (s.host) cudaFreeHost(s.host);
+        s.host = nullptr; s.used = 0;
+        s.cap = std::max<size_t>(need, 256 * 1024) * 2;
+        CU(cudaMallocHost(&s.host, s.cap));
+    }
+    *out = s.host + s.used;
+    s.used += (bytes + 255) & ~(size_t)255;
+    return RTB_OK;
+}
+/* a frame has been queued behind the uploads: close the arena, continue in the next one */
+int stage_rotate(rtb_ctx* ctx) {
+    RtbStageSlot& s = ctx->stage[ctx->stage_cur];
+    if (s.used == 0) return RTB_OK;
+    CU(cudaEventRecord(s.done, ctx->stream));
+    s.pending = true;
+    ctx->stage_cur = (ctx->stage_cur + 1) % RTB_STAGE_SLOTS;
+    return RTB_OK;
 }
 
 /* the strict build stages quaternion records, the fused build matrix records (rt_params.h) */
@@ -180,11 +174,13 @@ double algorithmic_flops(const rtb_stats& s) {
     return f;
 }
 
-int do_render(rtb_ctx* ctx, float* target, cudaStream_t st, bool counted, bool timed) {
+}  // namespace
+
+int rtb_do_render(rtb_ctx* ctx, float* target, bool target_global_rows, cudaStream_t st, bool counted, bool timed) {
     if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "null context");
     if (!ctx->have_defines) return fail(ctx, RTB_ERR_STATE, "rtb_render before rtb_set_defines (init_shaders)");
     const rtb_defines& d = ctx->defines;
-    if (ctx->shadow[RTB_BIND_SCENE].size() < sizeof(rtb_scene)) return fail(ctx, RTB_ERR_STATE, "scene_buf was never uploaded");
+    if (!ctx->have_scene) return fail(ctx, RTB_ERR_STATE, "scene_buf was never uploaded");
     const int counts[RTB_NUM_BINDINGS] = { 1, d.sphere_size, d.plane_size, d.surface_size, d.box_size, d.torus_size, d.ring_size,
                                            d.light_point_size, d.light_direct_size };
     for (int b = 0; b < RTB_NUM_BINDINGS; b++)
@@ -197,7 +193,7 @@ int do_render(rtb_ctx* ctx, float* target, cudaStream_t st, bool counted, bool t
     P.n_sphere = d.sphere_size; P.n_plane = d.plane_size; P.n_surf = d.surface_size; P.n_box = d.box_size; P.n_torus = d.torus_size;
     P.n_ring = d.ring_size; P.n_lpoint = d.light_point_size; P.n_ldirect = d.light_direct_size; P.iterations = d.iterations;
     for (int i = 0; i < 3; i++) { P.ambient[i] = round_through_percent_f(d.ambient_color[i]); P.shadow_ambient[i] = round_through_percent_f(d.shadow_ambient[i]); }
-    const rtb_scene* sc = (const rtb_scene*)ctx->shadow[RTB_BIND_SCENE].data();
+    const rtb_scene* sc = &ctx->scene_host;
     memcpy(P.cam_q, sc->quat_camera_rotation, 16);
     memcpy(P.cam_pos, sc->camera_pos, 12);
     P.canvas_w = sc->canvas_width; P.canvas_h = sc->canvas_height;
@@ -210,9 +206,9 @@ int do_render(rtb_ctx* ctx, float* target, cudaStream_t st, bool counted, bool t
     const bool strict = ctx->opt_strict != 0;
     P.lay = make_layout(d, strict);
     if (P.lay.total_bytes > ctx->packed_cap) {
-        if (ctx->packed) cudaFree(ctx->packed);
+        if (ctx->packed) CU(cudaFreeAsync(ctx->packed, ctx->stream));          /* stream-ordered: frames in flight keep their block */
         ctx->packed_cap = P.lay.total_bytes + 4096;
-        CU(cudaMalloc(&ctx->packed, ctx->packed_cap));
+        CU(cudaMallocAsync((void**)&ctx->packed, ctx->packed_cap, ctx->stream));
         ctx->dirty = true;
     }
     P.packed = ctx->packed;
@@ -221,7 +217,7 @@ int do_render(rtb_ctx* ctx, float* target, cudaStream_t st, bool counted, bool t
         P.tex[u].base = ctx->tex[u].dev; P.tex[u].w = ctx->tex[u].w; P.tex[u].h = ctx->tex[u].h; P.tex[u].levels = ctx->tex[u].levels;
         memcpy(P.tex[u].level_off, ctx->tex[u].off, sizeof ctx->tex[u].off);
     }
-    P.fb = target; P.rank = ctx->rank; P.world = ctx->world; P.block_rows = ctx->block_rows; P.local_rows = ctx->local_rows;
+    P.fb = target; P.fb_global = target_global_rows ? 1 : 0; P.rank = ctx->rank; P.world = ctx->world; P.block_rows = ctx->block_rows; P.local_rows = ctx->local_rows;
     P.tile_counter = ctx->tile_counter;
     P.n_tiles_x = (ctx->width + 7) / 8; P.n_tiles_y = (ctx->local_rows + 3) / 4;
     P.cull = ctx->opt_cull;
@@ -247,14 +243,18 @@ int do_render(rtb_ctx* ctx, float* target, cudaStream_t st, bool counted, bool t
     const int grid = ctx->n_sm * per_sm;                 /* persistent: a whole number of CTAs on every one of the SMs */
 
     if (getenv("RTB_DEBUG_TIMES") && kernel == RTB_KERNEL_PERSISTENT) {
-        if (!ctx->cta_times) CU(cudaMalloc(&ctx->cta_times, (size_t)grid * 5 * sizeof(unsigned long long)));
+        if (grid > ctx->cta_times_cap) {                  /* the grid depends on the build, the scene's shared-memory size and "ctas_per_sm" */
+            if (ctx->cta_times) { CU(cudaStreamSynchronize(st)); cudaFree(ctx->cta_times); ctx->cta_times = nullptr; }
+            CU(cudaMalloc(&ctx->cta_times, (size_t)grid * 5 * sizeof(unsigned long long)));
+            ctx->cta_times_cap = grid;
+        }
         CU(cudaMemsetAsync(ctx->cta_times, 0, (size_t)grid * 5 * sizeof(unsigned long long), st));
         ctx->cta_times_n = grid;
         P.cta_times = ctx->cta_times;
     }
-    if (st != ctx->stream) {                             /* uploads ran on the context stream: order them before this frame */
-        CU(cudaEventRecord(ctx->ev_upload, ctx->stream));
-        CU(cudaStreamWaitEvent(st, ctx->ev_upload, 0));
+    if (st != ctx->stream) {                             /* uploads (and allocations) ran on the context stream: order them before this frame */
+        CU(cudaEventRecord(ctx->ev_order, ctx->stream));
+        CU(cudaStreamWaitEvent(st, ctx->ev_order, 0));
     }
     if (ctx->dirty) {
         int pe = strict ? rtb_strict_launch_pack(&P, ctx->packed, st) : rtb_fast_launch_pack(&P, ctx->packed, st);
@@ -268,15 +268,20 @@ int do_render(rtb_ctx* ctx, float* target, cudaStream_t st, bool counted, bool t
                : rtb_fast_launch(&P, launch_kernel, counted ? 1 : 0, grid, threads, smem, st);
     if (e) return fail(ctx, RTB_ERR_CUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)e));
     if (timed) { CU(cudaEventRecord(ctx->ev1, st)); ctx->timed_pending = true; }
+    if (st != ctx->stream) {
+        /* ... and order the context stream behind this frame: the next upload overwrites the arrays the kernels are reading,
+         * the next frame reuses the packed block and the tile counter */
+        CU(cudaEventRecord(ctx->ev_order, st));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_order, 0));
+    }
+    { int rc_ = stage_rotate(ctx); if (rc_) return rc_; }
     ctx->stats.kernel_used = kernel; ctx->stats.grid = grid; ctx->stats.block = threads; ctx->stats.smem_bytes = (int)smem;
     return RTB_OK;
 }
 
-}  // namespace
-
 extern "C" {
 
-const char* rtb_version(void) { return "rtb200 0.1 (sm_100a)"; }
+const char* rtb_version(void) { return "rtb200 0.2 (sm_100a)"; }
 
 const char* rtb_last_error(const rtb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 
@@ -298,7 +303,9 @@ rtb_ctx* rtb_create(int width, int height, int device) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
-    if ((e = cudaEventCreateWithFlags(&ctx->ev_upload, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (int i = 0; i < RTB_STAGE_SLOTS; i++)
+        if ((e = cudaEventCreateWithFlags(&ctx->stage[i].done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->tile_counter, 256)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->counters, CNT_NUM * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
     ctx->local_rows = height;
@@ -309,8 +316,12 @@ rtb_ctx* rtb_create(int width, int height, int device) {
 
 void rtb_destroy(rtb_ctx* ctx) {
     if (!ctx) return;
+    for (rtb_ctx* p : ctx->peers) { p->root = nullptr; rtb_destroy(p); }
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    rtb_multi_release(ctx);
+    for (int i = 0; i < RTB_STAGE_SLOTS; i++) { if (ctx->stage[i].host) cudaFreeHost(ctx->stage[i].host); if (ctx->stage[i].done) cudaEventDestroy(ctx->stage[i].done); }
     for (int b = 0; b < RTB_NUM_BINDINGS; b++) if (ctx->raw[b]) cudaFree(ctx->raw[b]);
     if (ctx->packed) cudaFree(ctx->packed);
     if (ctx->tile_counter) cudaFree(ctx->tile_counter);
@@ -322,7 +333,7 @@ void rtb_destroy(rtb_ctx* ctx) {
     for (int u = 0; u < 6; u++) if (ctx->tex[u].dev) cudaFree(ctx->tex[u].dev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->ev_upload) cudaEventDestroy(ctx->ev_upload);
+    if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -332,7 +343,7 @@ int rtb_set_partition(rtb_ctx* ctx, int rank, int world, int block_rows) {
     if (world < 1 || rank < 0 || rank >= world || block_rows < 4 || (block_rows & 3))
         return fail(ctx, RTB_ERR_INVALID, "bad partition rank %d / world %d / block_rows %d (block_rows must be a multiple of 4)", rank, world, block_rows);
     ctx->rank = rank; ctx->world = world; ctx->block_rows = block_rows;
-    ctx->local_rows = compute_local_rows(ctx->height, rank, world, block_rows);
+    ctx->local_rows = rtb_compute_local_rows(ctx->height, rank, world, block_rows);
     return RTB_OK;
 }
 
@@ -343,39 +354,58 @@ int rtb_set_defines(rtb_ctx* ctx, const rtb_defines* d) {
     const int* c = &d->sphere_size;
     for (int i = 0; i < 8; i++) if (c[i] < 0 || c[i] > (1 << 20)) return fail(ctx, RTB_ERR_INVALID, "count %d out of range: %d", i, c[i]);
     if (d->iterations < 0) return fail(ctx, RTB_ERR_INVALID, "negative iterations");
+    for (rtb_ctx* p : ctx->peers) { int rc = rtb_set_defines(p, d); if (rc) return fail(ctx, rc, "%s", p->err.c_str()); }
     ctx->defines = *d;
     ctx->have_defines = true;
     ctx->dirty = true;
     return RTB_OK;
 }
 
-int rtb_upload(rtb_ctx* ctx, int binding, const void* data, size_t bytes) {
+namespace {
+/* stage the caller's bytes and queue the H2D copy; `replace` = glBufferData (the block holds exactly `bytes` afterwards),
+ * otherwise glBufferSubData(0, bytes) */
+int upload_block(rtb_ctx* ctx, int binding, const void* data, size_t bytes, bool replace) {
     if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "null context");
     if (binding < 0 || binding >= RTB_NUM_BINDINGS) return fail(ctx, RTB_ERR_INVALID, "unknown uniform-block binding %d", binding);
     if (bytes % ELEM_SIZE[binding]) return fail(ctx, RTB_ERR_INVALID, "binding %d: %zu bytes is not a multiple of the %zu-byte element", binding, bytes, ELEM_SIZE[binding]);
+    if (!replace && bytes > ctx->raw_bytes[binding])
+        return fail(ctx, RTB_ERR_INVALID, "binding %d: update of %zu bytes exceeds the block's %zu bytes (glBufferSubData: GL_INVALID_VALUE)", binding, bytes, ctx->raw_bytes[binding]);
+    for (rtb_ctx* p : ctx->peers) { int rc = upload_block(p, binding, data, bytes, replace); if (rc) return fail(ctx, rc, "%s", p->err.c_str()); }
     CU(cudaSetDevice(ctx->device));
-    if (bytes > ctx->raw_cap[binding] || !ctx->raw[binding]) {
-        if (ctx->raw[binding]) { CU(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->raw[binding]); ctx->raw[binding] = nullptr; }
+    if (replace && (bytes > ctx->raw_cap[binding] || !ctx->raw[binding])) {
+        /* stream-ordered free / allocate: frames already queued keep reading the old block, nothing synchronises */
+        if (ctx->raw[binding]) { CU(cudaFreeAsync(ctx->raw[binding], ctx->stream)); ctx->raw[binding] = nullptr; }
         size_t cap = bytes < 256 ? 256 : bytes;
-        CU(cudaMalloc(&ctx->raw[binding], cap));
+        CU(cudaMallocAsync(&ctx->raw[binding], cap, ctx->stream));
         ctx->raw_cap[binding] = cap;
     }
     if (data && bytes) {
-        /* pageable source: the runtime stages it before returning, so the caller may reuse `data` at once */
-        CU(cudaMemcpyAsync(ctx->raw[binding], data, bytes, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->shadow[binding].assign((const uint8_t*)data, (const uint8_t*)data + bytes);
-        ctx->raw_bytes[binding] = bytes;
-    } else if (bytes == 0) {
-        ctx->raw_bytes[binding] = 0;
-        ctx->shadow[binding].clear();
-    }   /* data == NULL with bytes > 0: allocation only (glBufferData(size, NULL)), contents arrive by a later upload */
+        uint8_t* host = nullptr;
+        int rc = stage_reserve(ctx, bytes, &host);
+        if (rc) return rc;
+        memcpy(host, data, bytes);                       /* the caller may reuse `data` as soon as we return */
+        CU(cudaMemcpyAsync(ctx->raw[binding], host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (binding == RTB_BIND_SCENE) { memcpy(&ctx->scene_host, data, sizeof(rtb_scene)); ctx->have_scene = true; }
+        /* an update may cover a prefix only: a texture reference seen earlier in the tail stays valid */
+        const bool refs = array_uses_textures(binding, data, bytes);
+        ctx->uses_tex[binding] = replace ? refs : (refs || (ctx->uses_tex[binding] && bytes < ctx->raw_bytes[binding]));
+    } else if (replace && bytes == 0) {
+        ctx->uses_tex[binding] = false;
+        if (binding == RTB_BIND_SCENE) ctx->have_scene = false;
+    }   /* data == NULL with bytes > 0: allocation only (glBufferData(size, NULL)), contents arrive by a later update */
+    if (replace) ctx->raw_bytes[binding] = bytes;
     ctx->dirty = true;
     return RTB_OK;
 }
+}  // namespace
+
+int rtb_upload(rtb_ctx* ctx, int binding, const void* data, size_t bytes) { return upload_block(ctx, binding, data, bytes, true); }
+int rtb_update(rtb_ctx* ctx, int binding, const void* data, size_t bytes) { return upload_block(ctx, binding, data, bytes, false); }
 
 int rtb_set_cubemap(rtb_ctx* ctx, const uint8_t* const faces[6], int w, int h, int channels) {
     if (!ctx || !faces) return fail(ctx, RTB_ERR_INVALID, "null argument");
     if (w <= 0 || h <= 0 || channels < 1 || channels > 4) return fail(ctx, RTB_ERR_INVALID, "bad cubemap %dx%dx%d", w, h, channels);
+    for (rtb_ctx* p : ctx->peers) { int rc = rtb_set_cubemap(p, faces, w, h, channels); if (rc) return fail(ctx, rc, "%s", p->err.c_str()); }
     CU(cudaSetDevice(ctx->device));
     size_t face_bytes = (size_t)w * h * 4;
     std::vector<uint8_t> rgba(face_bytes * 6);
@@ -399,9 +429,10 @@ int rtb_set_texture2d(rtb_ctx* ctx, int unit, const uint8_t* pixels, int w, int 
     if (!ctx || !pixels) return fail(ctx, RTB_ERR_INVALID, "null argument");
     if (unit < 1 || unit > 5) return fail(ctx, RTB_ERR_INVALID, "texture unit %d out of range 1..5", unit);
     if (w <= 0 || h <= 0 || channels < 1 || channels > 4) return fail(ctx, RTB_ERR_INVALID, "bad texture %dx%dx%d", w, h, channels);
+    for (rtb_ctx* p : ctx->peers) { int rc = rtb_set_texture2d(p, unit, pixels, w, h, channels); if (rc) return fail(ctx, rc, "%s", p->err.c_str()); }
     CU(cudaSetDevice(ctx->device));
     std::vector<uint8_t> chain;
-    Tex2D t;
+    RtbTex2D t;
     build_mip_chain(pixels, w, h, channels, chain, t);
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->tex[unit].dev) { cudaFree(ctx->tex[unit].dev); ctx->tex[unit].dev = nullptr; }
@@ -413,27 +444,34 @@ int rtb_set_texture2d(rtb_ctx* ctx, int unit, const uint8_t* pixels, int w, int 
 
 int rtb_set_option(rtb_ctx* ctx, const char* key, int value) {
     if (!ctx || !key) return fail(ctx, RTB_ERR_INVALID, "null argument");
+    if (strcmp(key, "gather")) for (rtb_ctx* p : ctx->peers) { int rc = rtb_set_option(p, key, value); if (rc) return fail(ctx, rc, "%s", p->err.c_str()); }
     if (!strcmp(key, "kernel")) { if (value < 0 || value > 2) return fail(ctx, RTB_ERR_INVALID, "kernel must be 0..2"); ctx->opt_kernel = value; }
     else if (!strcmp(key, "strict")) { if ((value ? 1 : 0) != ctx->opt_strict) ctx->dirty = true; ctx->opt_strict = value ? 1 : 0; }   /* the two builds stage different records */
     else if (!strcmp(key, "cull")) ctx->opt_cull = value ? 1 : 0;
     else if (!strcmp(key, "ctas_per_sm")) ctx->opt_ctas_per_sm = value;
     else if (!strcmp(key, "coop")) ctx->opt_coop = value ? 1 : 0;
+    else if (!strcmp(key, "gather")) { if (value != RTB_GATHER_NCCL && value != RTB_GATHER_P2P) return fail(ctx, RTB_ERR_INVALID, "gather must be 0 (NCCL) or 1 (P2P)");
+        if (value == RTB_GATHER_P2P && (ctx->peers.empty() || !ctx->p2p_ok)) return fail(ctx, RTB_ERR_STATE, "P2P gather needs a multi-device context whose GPUs have peer access to device 0");
+        ctx->opt_gather = value; }
     else return fail(ctx, RTB_ERR_INVALID, "unknown option '%s'", key);
     return RTB_OK;
 }
 
 int rtb_render(rtb_ctx* ctx) {
     if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "null context");
-    return do_render(ctx, ctx->fb, ctx->stream, false, true);
+    if (!ctx->peers.empty()) return rtb_multi_render(ctx);
+    return rtb_do_render(ctx, ctx->fb, false, ctx->stream, false, true);
 }
 
 int rtb_render_to(rtb_ctx* ctx, void* device_rgba32f, void* cuda_stream) {
     if (!ctx || !device_rgba32f) return fail(ctx, RTB_ERR_INVALID, "null argument");
-    return do_render(ctx, (float*)device_rgba32f, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, false, cuda_stream == nullptr);
+    if (!ctx->peers.empty()) return fail(ctx, RTB_ERR_STATE, "rtb_render_to on a multi-device context: use rtb_render + rtb_device_framebuffer");
+    return rtb_do_render(ctx, (float*)device_rgba32f, false, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, false, cuda_stream == nullptr);
 }
 
 int rtb_sync(rtb_ctx* ctx) {
     if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "null context");
+    for (rtb_ctx* p : ctx->peers) { int rc = rtb_sync(p); if (rc) return fail(ctx, rc, "%s", p->err.c_str()); }
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->cta_times && ctx->cta_times_n) {
@@ -472,12 +510,18 @@ int rtb_sync(rtb_ctx* ctx) {
         if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.kernel_ms = ms;
         ctx->timed_pending = false;
     }
+    if (ctx->frame_timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_f0, ctx->ev_f1) == cudaSuccess) ctx->frame_ms = ms;
+        ctx->frame_timed = false;
+    }
     return RTB_OK;
 }
 
 int rtb_render_counted(rtb_ctx* ctx, rtb_stats* out) {
     if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "null context");
-    int rc = do_render(ctx, ctx->fb, ctx->stream, true, false);
+    if (!ctx->peers.empty()) return fail(ctx, RTB_ERR_STATE, "rtb_render_counted on a multi-device context: count on a single-device one");
+    int rc = rtb_do_render(ctx, ctx->fb, false, ctx->stream, true, false);
     if (rc) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     unsigned long long c[CNT_NUM];
@@ -510,17 +554,18 @@ int rtb_read_rgba32f(rtb_ctx* ctx, float* dst) {
     if (!ctx || !dst) return fail(ctx, RTB_ERR_INVALID, "null argument");
     int rc = rtb_sync(ctx);
     if (rc) return rc;
-    CU(cudaMemcpy(dst, ctx->fb, (size_t)ctx->local_rows * ctx->width * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (ctx->fb_full) CU(cudaMemcpy(dst, ctx->fb_full, (size_t)ctx->height * ctx->width * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+    else CU(cudaMemcpy(dst, ctx->fb, (size_t)ctx->local_rows * ctx->width * 4 * sizeof(float), cudaMemcpyDeviceToHost));
     return RTB_OK;
 }
 
 int rtb_read_rgba8(rtb_ctx* ctx, uint8_t* dst) {
     if (!ctx || !dst) return fail(ctx, RTB_ERR_INVALID, "null argument");
     CU(cudaSetDevice(ctx->device));
-    const size_t n = (size_t)ctx->local_rows * ctx->width;
+    const size_t n = (size_t)(ctx->fb_full ? ctx->height : ctx->local_rows) * ctx->width;
     if (n == 0) return rtb_sync(ctx);
     if (!ctx->fb8) CU(cudaMalloc(&ctx->fb8, (size_t)ctx->width * ctx->height * 4));
-    rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const float4*)ctx->fb, (uchar4*)ctx->fb8, n);   /* after the frame, same stream */
+    rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const float4*)(ctx->fb_full ? ctx->fb_full : ctx->fb), (uchar4*)ctx->fb8, n);   /* after the frame, same stream */
     CU(cudaGetLastError());
     int rc = rtb_sync(ctx);
     if (rc) return rc;
@@ -528,6 +573,6 @@ int rtb_read_rgba8(rtb_ctx* ctx, uint8_t* dst) {
     return RTB_OK;
 }
 
-void* rtb_device_framebuffer(rtb_ctx* ctx) { return ctx ? ctx->fb : nullptr; }
+void* rtb_device_framebuffer(rtb_ctx* ctx) { return ctx ? (ctx->fb_full ? ctx->fb_full : ctx->fb) : nullptr; }
 
 }  // extern "C"

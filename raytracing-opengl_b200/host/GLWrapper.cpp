@@ -115,13 +115,17 @@ GLuint GLWrapper::getProgramId() { return 1; }
 /* src/GLWrapper.cpp:61-133: window + GL context  ->  CUDA context, stream and RGBA32F framebuffer */
 bool GLWrapper::init_window()
 {
-	ctx = rtb_create(width, height, env_int("RT_DEVICE", 0));
+	/* RT_GPUS=n: the frame is tile-partitioned over n GPUs of the box and gathered on device 0 inside draw() (one NCCL fan-in
+	 * per frame; RT_GATHER=1: the kernels store into device 0's frame over NVLink instead) */
+	const int n_gpus = env_int("RT_GPUS", 1);
+	ctx = n_gpus > 1 ? rtb_create_multi(width, height, n_gpus, env_int("RT_BLOCK_ROWS", 4)) : rtb_create(width, height, env_int("RT_DEVICE", 0));
 	if (!ctx) {
 		fprintf(stderr, "rtb_create failed: %s\n", rtb_last_error(nullptr));
 		return false;
 	}
 	rtb_set_option(ctx, "strict", env_int("RT_STRICT", 1));
 	rtb_set_option(ctx, "kernel", env_int("RT_KERNEL", 0));
+	if (n_gpus > 1 && rtb_set_option(ctx, "gather", env_int("RT_GATHER", 0))) die(ctx, "RT_GATHER");
 	window = rtb_shim_create_window(this, env_int("RT_FRAMES", 1));
 	printf("rtb200 %s, %dx%d\n", rtb_version(), width, height);
 	return true;
@@ -227,7 +231,7 @@ void GLWrapper::update_buffer(GLuint ubo, size_t size, void* data)
 {
 	auto it = g_ubos.find(ubo);
 	if (it == g_ubos.end()) { fprintf(stderr, "update_buffer: unknown ubo %u\n", ubo); exit(1); }
-	if (rtb_upload(it->second.first, it->second.second, data, size)) die(it->second.first, "update_buffer");
+	if (rtb_update(it->second.first, it->second.second, data, size)) die(it->second.first, "update_buffer");
 	dump_block(it->second.second, data, size);
 }
 

@@ -18,11 +18,15 @@ colour to the 1e-4 tolerance at all.  The criterion separates those pixels from 
     a fused pixel PASSES when  |fused(p) - oracle32(p)| <= TOL  or  p is not determined.
     AVOIDABLE OUTLIER = a determined pixel the fused build misses by more than TOL.  The tests demand zero.
 
-Why TOL/4 and why the exaggerated members: a finite ensemble must not blame a correct implementation.  A pixel with a
-continuous sensitivity sigma ~ TOL/2 would slip through a TOL/2 gate with probability ~1e-2 and then be missed by a correct
-implementation with probability ~5e-2; at TOL/4 both factors collapse.  A pixel that sits within an ulp of a discrete flip
-flips in any single conformant evaluation with a probability well below 1/2, so K1 = 4 members overlook it often; under
-+-AMP-ulp noise the flip probability saturates near 1/2 per member and K2 = 8 members overlook it with probability 2^-8.
+Why TOL/4, K1 = 16 and the exaggerated members: a finite ensemble must not blame a correct implementation.
+  * A pixel with a continuous sensitivity sigma ~ TOL/2 would slip through a TOL/2 gate with probability ~1e-2 and then be
+    missed by a correct implementation with probability ~5e-2; at TOL/4 both factors collapse.
+  * Discrete flips come in two kinds.  Threshold margins (a ray grazing a silhouette or a shadow edge within a few ulps) flip
+    more often the larger the noise: the K2 = 4 members with +-AMP = 8 ulps per operation catch those.  The other kind only
+    happens in a band about one ulp wide — exact ties such as tN == tF of a ray through a box edge, or the exact zero that
+    feeds the box test's NaN quirk (rt.frag:417-423): 1-ulp rounding changes reach them in ~1/3 of the evaluations, larger
+    noise jumps over them (measured: flip frequency 0.33 at 1 ulp, 0.08 at 2-4 ulps, 0.016 at 8-16, 0 at 64).  Only many
+    conformant members find those, hence K1 = 16: a pixel that flips with probability 1/3 is overlooked with 0.67^16 = 0.2 %.
 The price is coverage: pixels whose path survives 1-ulp but not AMP-ulp noise are excluded although implementations agree on
 them.  Both fractions are reported (frac_within_tol is the raw agreement with oracle32, frac_undetermined the excluded part).
 
@@ -44,8 +48,8 @@ CASES = {
     "default1080": ("default1080", 1 / 8),
     "spheres4k": ("spheres4k", 1 / 16),
     "tori1080": ("tori1080", 1 / 10),
-    "mixed1024_4k": ("mixed1024_4k", 1 / 24),
-    "mixed1024_8k": ("mixed1024_8k", 1 / 48),
+    "mixed1024_4k": ("mixed1024_4k", 1 / 20),
+    "mixed1024_8k": ("mixed1024_8k", 1 / 48),     # the same scene as mixed1024_4k, sampled on a different pixel grid
 }
 
 
@@ -67,7 +71,7 @@ def pix_err(a, b):
     return d.max(axis=-1)
 
 
-K1, K2, AMP = 4, 8, 16
+K1, K2, AMP = 16, 4, 8
 
 
 def ensemble(sc, ts, k1=K1, k2=K2, amp=AMP, quads=None, window=None, threads=0):
@@ -119,11 +123,13 @@ def fixture_path(name):
     return os.path.join(FIXTURES, name + ".npz")
 
 
-def save_fixture(name, sc, spread, pathdiff):
+def save_fixture(name, sc, spread, pathdiff, calibration=()):
+    """calibration: avoidable-outlier counts of independent conformant samples under this fixture (make_envelope.py)"""
     os.makedirs(FIXTURES, exist_ok=True)
     h, w = spread.shape
     np.savez_compressed(fixture_path(name), spread=np.minimum(spread, 6e4).astype(np.float16), pathdiff=np.packbits(pathdiff.ravel()),
-                        shape=np.array([h, w], dtype=np.int32), ensemble=np.array([K1, K2, AMP], dtype=np.int32), digest=np.array(scene_digest(sc)))
+                        shape=np.array([h, w], dtype=np.int32), ensemble=np.array([K1, K2, AMP], dtype=np.int32), digest=np.array(scene_digest(sc)),
+                        calibration=np.array(list(calibration), dtype=np.int32))
 
 
 def load_fixture(name):
@@ -134,3 +140,13 @@ def load_fixture(name):
     pathdiff = np.unpackbits(z["pathdiff"])[: h * w].astype(bool).reshape(h, w)
     cfg, scale = CASES[name]
     return cfg, scale, spread, pathdiff, str(z["digest"])
+
+
+def fixture_calibration(name):
+    return [int(x) for x in np.load(fixture_path(name))["calibration"]]
+
+
+# A finite ensemble cannot push the blame rate of a correct implementation to exactly zero: a pixel that flips with probability p per
+# evaluation is overlooked by K1 members and then hit by the implementation under test with probability p (1 - p)^K1 <= 1 / (e K1).
+# Independent conformant samples score 0-1 avoidable outliers per fixture (stored in the fixtures); the tests allow this many.
+ALLOWANCE = 3

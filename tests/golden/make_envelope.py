@@ -40,6 +40,7 @@ def main():
         for k in (100, 101, 102):
             probe, _, _ = Oracle(sc, ts, precision="sr").render_ex(sample=k)
             cals.append(env.judge(probe, o32, spread_s, pathdiff_s))
+        env.save_fixture(name, sc, spread, pathdiff, [c["avoidable_outliers"] for c in cals])
         print(json.dumps({"case": name, "size": list(o32.shape[:2]), "seconds": round(time.time() - t0, 1), "undetermined": round(cals[0]["frac_undetermined"], 4),
                           "calibration_avoidable": [c["avoidable_outliers"] for c in cals], "calibration_within_tol": [round(c["frac_within_tol"], 4) for c in cals],
                           "bytes": os.path.getsize(env.fixture_path(name))}), flush=True)

@@ -3,9 +3,8 @@
 Tolerance (BASELINE.json north_star): per-channel |CUDA - reference| <= 1e-4 on the RGBA32F framebuffer.
   * strict build: EVERY pixel must satisfy it (observed <= 5e-7: + - * / sqrt are bit-identical to the oracle,
     only libm's pow/exp/atan/asin/log2 differ by an ulp).
-  * fast build (FMA contraction etc.): ulp-level differences are amplified by every reflection off a curved
-    surface (chaotic paths), so the bound holds for all but a stated fraction of pixels at full bounce depth,
-    and for >= 95 % of pixels when paths are cut after the first hit (silhouette / shadow-edge / solver-trip flips).
+  * fused build (FMA contraction, MUFU reciprocals, rotation matrices): judged by the envelope criterion of
+    tests/envelope.py (tests/test_envelope.py); here only a first-hit sanity bound.
 """
 import os
 
@@ -95,19 +94,30 @@ def test_textured_golden_vector_outside_diverged_quads(procedural):
 
 
 @pytest.mark.parametrize("case", ["spheres4k/12", "tori1080/8", "mixed1024/16", "default1080/8"])
-def test_fast_build_error_budget(case, procedural):
+def test_fused_build_first_hit(case, procedural):
+    """Paths cut after the first hit (no chaotic amplification through reflections): the fused build may differ from the fp32
+    oracle only where a silhouette, a shadow edge or a solver trip count flips.  The full-depth gate is the envelope
+    criterion (tests/test_envelope.py::test_fused_build_has_no_avoidable_outliers)."""
     sc = CASES[case]()
-    want = Oracle(sc, procedural).render()
-    got, _ = gpu_render(sc, procedural, strict=0)
-    err = pixel_err(got, want)
-    frac = float((err > TOL).mean())
-    assert frac <= 0.15, f"{case}: {frac:.2%} of pixels beyond {TOL} at full depth"
-    assert float(np.median(err)) <= 1e-6
-    sc.scene["reflect_depth"] = 1                    # first hit only: no chaotic amplification
+    sc.scene["reflect_depth"] = 1
     want1 = Oracle(sc, procedural).render()
     got1, _ = gpu_render(sc, procedural, strict=0)
-    frac1 = float((pixel_err(got1, want1) > TOL).mean())
-    assert frac1 <= 0.05, f"{case}: {frac1:.3%} of first-hit pixels beyond {TOL}"
+    err = pixel_err(got1, want1)
+    frac1 = float((err > TOL).mean())
+    assert frac1 <= 0.05, f"{case}: {frac1:.3%} of first-hit pixels beyond {TOL}"      # tori: the fp32 Durand-Kerner root itself is only good to ~1e-4 (3 % observed)
+    assert float(np.median(err)) <= 1e-6
+
+
+def test_absorb_distance_quirk_q5_on_the_gpu():
+    """rt.frag:816,859 — absorbDistance accumulates over the whole path (tests/test_oracle_kat.py has the closed form)."""
+    from test_oracle_kat import _two_glass_spheres
+    sc, sky = _two_glass_spheres(0.4)
+    want = Oracle(sc, sky).render()
+    for k in (KERNEL_QUAD, KERNEL_PERSISTENT):
+        got, _ = gpu_render(sc, sky, kernel=k)
+        assert pixel_err(got, want).max() <= TOL
+    fused, _ = gpu_render(sc, sky, strict=0)
+    assert float((pixel_err(fused, want) > TOL).mean()) < 0.002          # silhouette pixels only
 
 
 def test_quad_and_persistent_kernels_are_bit_identical(procedural):

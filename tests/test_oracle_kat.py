@@ -232,3 +232,75 @@ def test_glass_sphere_path_terminates():
     sc.spheres.append(SM.create_sphere((0, 0, 2), 1.5, SM.create_material((1, 1, 1), 200, 0.1, 1.125, (1, 0, 2), 1), True))
     img = Oracle(sc).render()
     assert np.isfinite(img).all()
+
+
+def _two_glass_spheres(absorb=0.4):
+    """camera on the z axis, two absorbing glass spheres of index 1 (no bending, no Fresnel reflection on the axis), uniform sky"""
+    from rtb200.textures import TextureSet
+    sc = empty(512, 512, 4)
+    glass = SM.create_material((1, 1, 1), 0, 0.0, refract=1.0, absorb=(absorb, absorb, absorb))
+    sc.spheres.append(SM.create_sphere((0, 2, 0), 1.0, glass, hollow=True))     # hollow: the far root is returned from inside (rt.frag:350)
+    sc.spheres.append(SM.create_sphere((0, 2, 6), 1.5, glass, hollow=True))
+    sky = TextureSet(cube=[np.full((8, 8, 3), 200, dtype=np.uint8) for _ in range(6)])
+    return sc, sky
+
+
+def test_absorb_distance_accumulates_over_the_whole_path():
+    """Quirk Q5 (rt.frag:816,859): absorbDistance is initialised once per pixel and only ever grows — the second glass body
+    attenuates by exp(-absorb * (d1 + d2)), not by exp(-absorb * d2)."""
+    a = 0.4
+    sc, sky = _two_glass_spheres(a)
+    px = Oracle(sc, sky).render_quads([256], [256])[0, 0, :3]          # the pixel next to the optical axis
+    # chords of that pixel's ray through the two spheres, in fp64
+    rd = np.array([0.5 / 512, 0.5 / 512, 1.0]); rd /= np.linalg.norm(rd)
+    ro = np.array([0.0, 2.0, -12.0])
+
+    def chord(c, r):
+        oc = ro - np.array(c, dtype=float)
+        b = oc @ rd
+        return 2.0 * math.sqrt(b * b - (oc @ oc - r * r))
+
+    d1, d2 = chord((0, 2, 0), 1.0), chord((0, 2, 6), 1.5)
+    sky_c = 200 / 255
+    cumulative = sky_c * math.exp(-a * d1) * math.exp(-a * (d1 + d2))
+    reset = sky_c * math.exp(-a * d1) * math.exp(-a * d2)
+    assert abs(reset - cumulative) > 0.05                               # the two readings are far apart ...
+    assert np.allclose(px, cumulative, atol=3e-3), (px, cumulative, reset)   # ... and the shader's is the cumulative one (bias offsets ~1e-3)
+
+
+def test_update_buffers_never_resends_the_directional_lights(procedural):
+    """Quirk Q10 (SceneManager.cpp:254 vs :266-276): lights_direct_buf is written by init_buffers only; update_buffers, which
+    runs every frame, sends the other eight blocks.  A drop-in must keep the init-time bytes — checked here on the host logic
+    of the Python mirror (the C++ host inherits it from the reference's unchanged SceneManager.cpp)."""
+    import rtb200
+    sent = []
+
+    class Recorder(rtb200.GLWrapper):
+        def init_window(self):
+            return True
+
+        def init_shaders(self, d):
+            pass
+
+        def load_cubemap(self, faces, genMipmap=False):
+            return 1
+
+        def load_texture(self, *a, **k):
+            return 1
+
+        def init_buffer(self, name, bindingPoint, data):
+            sent.append(("init", name))
+            return len(sent)
+
+        def update_buffer(self, ubo, data):
+            sent.append(("update", ubo))
+
+    sc = scenes.default_scene(64, 48, 2)
+    gl = Recorder(64, 48)
+    handles = rtb200.setup_scene(gl, sc, procedural)
+    assert ("init", "lights_direct_buf") in sent
+    sent.clear()
+    rtb200.update_buffers(gl, sc, handles)                             # SceneManager::update_buffers, SceneManager.cpp:266-276
+    updated = {h for kind, h in sent if kind == "update"}
+    assert handles["lights_direct_buf"] not in updated
+    assert updated == {handles[n] for n in handles if n != "lights_direct_buf" and (n == "scene_buf" or len(sc.array(n[:-4])))}

@@ -38,7 +38,12 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 srows = list(csv.reader(src.splitlines()))
 hdr = next(x for x in srows if x and x[0] == "Address")
 ie = hdr.index("Instructions Executed")
+te = hdr.index("Thread Instructions Executed")
 n_p = n_s = n_all = 0.0
+# executed fp32 flops = what the FMA pipe really did (thread level): FFMA 2, FMUL / FADD 1, packed forms twice that.  Reported next to
+# the ALGORITHMIC flops of roofline.achieved so that strength reduction cannot pass as utilisation (and vice versa).
+FLOPS = {"FFMA": 2, "FMUL": 1, "FADD": 1, "FFMA2": 4, "FMUL2": 2, "FADD2": 2}
+executed_flops = 0.0
 for x in srows:
     if len(x) != len(hdr) or x[0] == "Address":
         continue
@@ -47,12 +52,13 @@ for x in srows:
         continue
     n = float(x[ie] or 0)
     n_all += n
-    if m.group(1) == "FFMA2":
+    executed_flops += FLOPS.get(m.group(1), 0) * float(x[te] or 0)
+    if m.group(1) in ("FFMA2", "FMUL2", "FADD2"):
         n_p += n
     elif m.group(1) in ("FFMA", "FMUL", "FADD", "IMAD", "HFMA2"):
         n_s += n
 cycles = val("smsp__cycles_active.sum")
-entry.update({"warp_inst_ffma2": int(n_p), "warp_inst_fma_pipe_scalar": int(n_s), "warp_inst_other": int(n_all - n_p - n_s),
+entry.update({"executed_fp32_flops": executed_flops, "warp_inst_ffma2": int(n_p), "warp_inst_fma_pipe_scalar": int(n_s), "warp_inst_other": int(n_all - n_p - n_s),
               "smsp_cycles_active": int(cycles), "fma_pipe_cycles_frac": round((n_s + 2 * n_p) / cycles, 4),
               "issue_cycles_frac": round((n_all + n_p) / cycles, 4)})
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
