@@ -14,6 +14,13 @@
 #ifndef RTB_SCALAR_DK
 #define RTB_SCALAR_DK 0
 #endif
+/* tests per trip of the quadric and box loops (A/B switch; `#pragma unroll` takes no macro, hence _Pragma) */
+#ifndef RTB_SCAN_UNROLL
+#define RTB_SCAN_UNROLL 1
+#endif
+#define RTB_STR_(x) #x
+#define RTB_STR(x) RTB_STR_(x)
+#define RTB_UNROLL_SCAN _Pragma(RTB_STR(unroll RTB_SCAN_UNROLL))
 
 namespace RTB_NS {
 
@@ -89,6 +96,7 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
         }
 #undef RTB_SPHERE_FINISH
     }
+    RTB_UNROLL_SCAN
     for (int i = 0; i < P.n_surf; i++) {
         if (on) {
             if (intersectSurface(K, ro, rd, S.surfs + i, tmin, t)) {
@@ -96,7 +104,7 @@ DEV void scan_scene(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, 
             }
         }
     }
-#pragma unroll 1
+    RTB_UNROLL_SCAN
     for (int i = 0; i < P.n_box; i++) {
         if (on) {
             if (intersectBox(K, ro, rd, S.boxes + i, tmin, t)) {

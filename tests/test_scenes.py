@@ -7,6 +7,8 @@ import pytest
 from rtb200 import scenes
 from rtb200.scene import rt_sphere
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_pcg32_reference_vector():
     """O'Neill's pcg32 demo: seed 42, stream 54 -> 0xa15c02b7 0x7b47f409 0xba1d3330 ..."""
@@ -83,3 +85,25 @@ def test_default_scene_equals_the_dump_of_the_unchanged_main_cpp():
         assert np.allclose(a, b, rtol=3e-7, atol=1e-30), name
     scene = np.frombuffer(z["scene"].tobytes(), dtype=S.rt_scene)[0]
     assert np.allclose(scene["quat_camera_rotation"], sc.scene["quat_camera_rotation"]) and np.allclose(scene["camera_pos"], sc.scene["camera_pos"])
+
+
+def test_cpp_scene_generator_produces_the_same_bytes(tmp_path):
+    """the workload generator lives in Python (scenes.py) and in C++ (host/scene_gen.cpp); the two must agree byte
+    for byte on every uniform block, at full size, for every synthetic BASELINE config."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    src = os.path.join(ROOT, "raytracing-opengl_b200", "host", "scene_gen.cpp")
+    exe = tmp_path / "rt_scene_gen"
+    subprocess.check_call(["g++", "-O2", "-std=c++11", "-ffp-contract=off", "-DRTB_SCENE_GEN_MAIN", "-o", str(exe), src])
+    for config in ("spheres4k", "tori1080", "mixed1024_4k", "mixed1024_8k"):
+        d = tmp_path / config
+        d.mkdir()
+        subprocess.check_call([str(exe), config, "0", "0", "0", str(d)])
+        sc = scenes.build_config(config)
+        assert (d / "scene_buf.bin").read_bytes() == np.ascontiguousarray(sc.scene).tobytes(), config
+        assert (d / "defines.bin").read_bytes() == sc.get_defines().tobytes(), config
+        for blk, attr in (("spheres_buf", "spheres"), ("planes_buf", "planes"), ("surfaces_buf", "surfaces"), ("boxes_buf", "boxes"), ("toruses_buf", "toruses"),
+                          ("rings_buf", "rings"), ("lights_point_buf", "lights_point"), ("lights_direct_buf", "lights_direct")):
+            assert (d / (blk + ".bin")).read_bytes() == sc.array(attr).tobytes(), (config, blk)
