@@ -148,6 +148,22 @@ int rtb_set_option(rtb_ctx* ctx, const char* key, int value);
  * from the current buffers into the context's device framebuffer.  Asynchronous. */
 int rtb_render(rtb_ctx* ctx);
 
+/* ---- SMAA post-pass -------------------------------------------------------------------------
+ * GLWrapper::enable_SMAA(preset)  (GLWrapper.h:30; GLWrapper.cpp:149-153): preset 0..3 = LOW, MEDIUM, HIGH, ULTRA
+ * (SMAA_Builder.h:9-12; main.cpp:32 uses ULTRA), -1 = off (the default of this library).  When on, rtb_render() follows
+ * the ray-trace pass with the reference's three passes (GLWrapper.cpp:173-204: luma edge detection, blending weights,
+ * neighbourhood blending) on the RGBA8-quantised frame, and rtb_read_rgba8() returns the post-processed image
+ * (rtb_read_rgba32f() keeps returning the ray-traced floats).  Not applied by rtb_render_to(). */
+int rtb_enable_smaa(rtb_ctx* ctx, int preset);
+/* SMAA_Builder::load_area_texture / load_search_texture  (SMAA_Builder.h:45-79): the precomputed lookup tables of
+ * src/AreaTex.h (RG8, 160 x 560) and src/SearchTex.h (R8, 64 x 16), rows in file order.  The library ships no copy of them. */
+int rtb_smaa_set_tables(rtb_ctx* ctx, const uint8_t* area_rg8, const uint8_t* search_r8);
+/* The three passes alone on a host RGBA8 image of the context's size (tests, measurements).  Any output may be NULL:
+ * out RGBA8, edges RG8, blend RGBA8; *ms = CUDA-event time of the three kernels. */
+int rtb_smaa_apply(rtb_ctx* ctx, const uint8_t* rgba8, uint8_t* out_rgba8, uint8_t* edges_rg8, uint8_t* blend_rgba8, float* ms);
+/* CUDA-event time of the SMAA passes of the last frame / rtb_smaa_apply. */
+int rtb_smaa_last_ms(rtb_ctx* ctx, float* ms);
+
 /* Same, into a caller-owned DEVICE buffer (local_rows*W*4 floats) on a caller
  * stream (cudaStream_t passed as void*; NULL = the context's stream). */
 int rtb_render_to(rtb_ctx* ctx, void* device_rgba32f, void* cuda_stream);

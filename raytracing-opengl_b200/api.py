@@ -23,6 +23,7 @@ LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "librtb200.so")  
 
 KERNEL_AUTO, KERNEL_QUAD, KERNEL_PERSISTENT = 0, 1, 2
 GATHER_NCCL, GATHER_P2P = 0, 1
+SMAA_LOW, SMAA_MEDIUM, SMAA_HIGH, SMAA_ULTRA = 0, 1, 2, 3        # enum SMAA_PRESET, SMAA_Builder.h:9-12
 COMM_ID_BYTES = 128
 
 
@@ -75,6 +76,10 @@ def load_library() -> C.CDLL:
     L.rtb_comm_unique_id.argtypes = [vp]
     L.rtb_comm_init.argtypes = [vp, vp, i, i, i]
     L.rtb_gather.argtypes = [vp, vp, vp, vp]
+    L.rtb_enable_smaa.argtypes = [vp, i]
+    L.rtb_smaa_set_tables.argtypes = [vp, vp, vp]
+    L.rtb_smaa_apply.argtypes = [vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
+    L.rtb_smaa_last_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.rtb_set_cubemap.argtypes = [vp, C.POINTER(vp), i, i, i]
     L.rtb_set_texture2d.argtypes = [vp, i, vp, i, i, i]
     L.rtb_set_option.argtypes = [vp, C.c_char_p, i]
@@ -145,9 +150,35 @@ class GLWrapper:
             raise RtbError(self._L.rtb_last_error(None).decode())
         return True
 
-    # -- GLWrapper.h:30: SMAA is out of scope (BASELINE.json north_star); accepted and ignored
-    def enable_SMAA(self, preset=None):
-        pass
+    # -- GLWrapper.h:30  (GLWrapper.cpp:149-153).  preset: SMAA_PRESET 0..3 = LOW, MEDIUM, HIGH, ULTRA; None / -1 switches it off.
+    #    The lookup tables (src/AreaTex.h, src/SearchTex.h) must have been handed over with smaa_set_tables().
+    def enable_SMAA(self, preset=SMAA_ULTRA):
+        self._check(self._L.rtb_enable_smaa(self._ctx, -1 if preset is None else int(preset)))
+
+    # -- SMAA_Builder::load_area_texture / load_search_texture (SMAA_Builder.h:45-79): RG8 [560,160,2] and R8 [16,64]
+    def smaa_set_tables(self, area, search):
+        a = np.ascontiguousarray(area, dtype=np.uint8)
+        s = np.ascontiguousarray(search, dtype=np.uint8)
+        if a.size != 160 * 560 * 2 or s.size != 64 * 16:
+            raise RtbError("AreaTex is 160x560 RG8, SearchTex 64x16 R8")
+        self._check(self._L.rtb_smaa_set_tables(self._ctx, a.ctypes.data, s.ctypes.data))
+
+    def smaa_apply(self, rgba8):
+        """The three SMAA passes alone on an RGBA8 image [H, W, 4] of the context's size: (out, edges [H,W,2], blend [H,W,4], ms)."""
+        img = np.ascontiguousarray(rgba8, dtype=np.uint8)
+        if img.shape != (self.height, self.width, 4):
+            raise RtbError(f"image must be [{self.height}, {self.width}, 4]")
+        out = np.empty_like(img)
+        edges = np.empty((self.height, self.width, 2), dtype=np.uint8)
+        blend = np.empty_like(img)
+        ms = C.c_float(0)
+        self._check(self._L.rtb_smaa_apply(self._ctx, img.ctypes.data, out.ctypes.data, edges.ctypes.data, blend.ctypes.data, C.byref(ms)))
+        return out, edges, blend, float(ms.value)
+
+    def smaa_last_ms(self) -> float:
+        ms = C.c_float(0)
+        self._check(self._L.rtb_smaa_last_ms(self._ctx, C.byref(ms)))
+        return float(ms.value)
 
     # -- GLWrapper.h:26  (GLWrapper.cpp:232-247)
     def init_shaders(self, defines):

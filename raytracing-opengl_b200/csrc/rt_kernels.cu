@@ -67,8 +67,29 @@ DEV int global_row(const FrameParams& P, int ly) {
 }
 
 /* ------------------------------------------------------------------ quad kernel */
+/* The quad kernel scans the scene from three places (main path, getReflectedColor, the light loop).  Inlined three times the
+ * kernel is ~45 KB of SASS and, with 16 warps per SM at 16 different places of it, instruction-fetch bound: ncu shows
+ * `stalled_no_instruction` 4.7 warps per issue and issue slots 46 % busy on the default scene
+ * (profiles/r2_ncu_default1080_fused_quad_kernel.txt).  RTB_QUAD_SCAN_CALL=1 (default) makes the scan ONE function that is called. */
+#ifndef RTB_QUAD_SCAN_CALL
+#define RTB_QUAD_SCAN_CALL 1                    /* measured: default1080 fused 1.107 -> 0.936 ms, strict 2.43 -> 2.13 ms (profiles/r2_quad_scan_call_ab.jsonl) */
+#endif
+#ifndef QUAD_MIN_BLOCKS
+#define QUAD_MIN_BLOCKS 1
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(QUAD_THREADS) quad_kernel(const __grid_constant__ FrameParams P) {
+#if RTB_QUAD_SCAN_CALL
+__device__ __noinline__
+#else
+DEV
+#endif
+void scan_quad(const FrameParams& P, const SceneView& S, vec3 ro, vec3 rd, bool active, bool shadow_mode, float limit, int ctx,
+               float& tmin_out, int& id_out, float& shadow_out, vec2& ring_uv_out, Counters& cnt) {
+    scan_scene<COUNT, true, true>(P, S, ro, rd, active, shadow_mode, limit, ctx, tmin_out, id_out, shadow_out, ring_uv_out, cnt);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(QUAD_THREADS, QUAD_MIN_BLOCKS) quad_kernel(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar;
     stage_scene_tma(smem, &mbar, P.packed, P.lay.total_bytes);
@@ -105,7 +126,7 @@ __global__ void __launch_bounds__(QUAD_THREADS) quad_kernel(const __grid_constan
 
         while (__any_sync(FULL, alive)) {                   /* one loop trip of rt.frag:821, all lanes together */
             float tm, sh_unused; int id; vec2 ruv;
-            scan_scene<COUNT, true, true>(P, S, ro, rd, alive, false, MAX_DIST, 0, tm, id, sh_unused, ruv, *cp);
+            scan_quad<COUNT>(P, S, ro, rd, alive, false, MAX_DIST, 0, tm, id, sh_unused, ruv, *cp);
             bool hit = alive && tm < MAX_DIST;
             if (alive && !hit) {                            /* rt.frag:892-895 */
                 color = color + texture_cube(P.cube, rd) * mask;
@@ -141,7 +162,7 @@ __global__ void __launch_bounds__(QUAD_THREADS) quad_kernel(const __grid_constan
             Material mat2 = {}; vec3 n2 = mk3(0.f, 0.f, 0.f); vec3 spt2 = sro;
             if (__any_sync(FULL, sub)) {
                 float t2; int id2; vec2 ruv2;
-                scan_scene<COUNT, true, true>(P, S, sro, srd, sub, false, MAX_DIST, 1, t2, id2, sh_unused, ruv2, *cp);
+                scan_quad<COUNT>(P, S, sro, srd, sub, false, MAX_DIST, 1, t2, id2, sh_unused, ruv2, *cp);
                 bool sub_light = sub && id2 >= 0 && id_type(id2) == RTB_TYPE_POINT_LIGHT;
                 bool hit2 = sub && !sub_light && t2 < MAX_DIST;
                 vec3 pt2 = sro + srd * t2;
@@ -165,7 +186,7 @@ __global__ void __launch_bounds__(QUAD_THREADS) quad_kernel(const __grid_constan
                 for (int l = 0; l < n_lights; l++) {
                     LightSample L = light_sample(P, l, s_pt);
                     float tdummy, shadow; int iddummy; vec2 uvdummy;
-                    scan_scene<COUNT, true, true>(P, S, s_pt, L.dir_n, do_shade, true, L.dist, sub_shade ? 1 : 0, tdummy, iddummy, shadow, uvdummy, *cp);
+                    scan_quad<COUNT>(P, S, s_pt, L.dir_n, do_shade, true, L.dist, sub_shade ? 1 : 0, tdummy, iddummy, shadow, uvdummy, *cp);
                     if (do_shade) {
                         if (COUNT) cp->light_evals++;
                         shade_light(P, L, shadow, s_rd, s_col, s_dif, s_spec, s_n, diffuse, specular);

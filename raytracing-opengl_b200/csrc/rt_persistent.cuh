@@ -27,10 +27,11 @@
 #pragma once
 #include "rt_scan.cuh"
 /* GATE (rt_scan.cuh): skip the tests of lanes without a live path.  Idle lanes exist only in the last trips of a frame (the cooperative
- * drain takes over), so the fused build, whose tests are 3-4x shorter, drops the 4-instruction branch region per test: idle lanes re-scan
- * their last ray and the result is dropped (mixed1024@4K 246.4 -> 240.1 ms, spheres4k 19.5 -> 18.4 ms).  The strict build keeps it. */
+ * drain takes over), so the 4-instruction branch region per test is dropped: idle lanes re-scan their last ray and the result is
+ * dropped (fused build: mixed1024@4K 246.4 -> 240.1 ms, spheres4k 19.5 -> 18.4 ms; strict build, together with the shared-window
+ * addressing: 388.5 -> 382.9 ms, 31.15 -> 28.85 ms; profiles/r2_strict_gate_saddr_ab.jsonl). */
 #ifndef RTB_PERSIST_GATE
-#define RTB_PERSIST_GATE (RTB_STRICT != 0)
+#define RTB_PERSIST_GATE false
 #endif
 
 namespace RTB_NS {

@@ -321,6 +321,7 @@ void rtb_destroy(rtb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     rtb_multi_release(ctx);
+    rtb_smaa_release(ctx);
     for (int i = 0; i < RTB_STAGE_SLOTS; i++) { if (ctx->stage[i].host) cudaFreeHost(ctx->stage[i].host); if (ctx->stage[i].done) cudaEventDestroy(ctx->stage[i].done); }
     for (int b = 0; b < RTB_NUM_BINDINGS; b++) if (ctx->raw[b]) cudaFree(ctx->raw[b]);
     if (ctx->packed) cudaFree(ctx->packed);
@@ -459,8 +460,14 @@ int rtb_set_option(rtb_ctx* ctx, const char* key, int value) {
 
 int rtb_render(rtb_ctx* ctx) {
     if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "null context");
+    ctx->smaa_valid = false;
     if (!ctx->peers.empty()) return rtb_multi_render(ctx);
-    return rtb_do_render(ctx, ctx->fb, false, ctx->stream, false, true);
+    int rc = rtb_do_render(ctx, ctx->fb, false, ctx->stream, false, true);
+    if (rc == RTB_OK && ctx->smaa_preset >= 0 && ctx->world == 1) {      /* GLWrapper.cpp:173-204: the three SMAA draws follow the ray-trace draw */
+        rc = rtb_smaa_after_frame(ctx, ctx->fb, ctx->stream);
+        ctx->smaa_valid = rc == RTB_OK;
+    }
+    return rc;
 }
 
 int rtb_render_to(rtb_ctx* ctx, void* device_rgba32f, void* cuda_stream) {
@@ -564,6 +571,12 @@ int rtb_read_rgba8(rtb_ctx* ctx, uint8_t* dst) {
     CU(cudaSetDevice(ctx->device));
     const size_t n = (size_t)(ctx->fb_full ? ctx->height : ctx->local_rows) * ctx->width;
     if (n == 0) return rtb_sync(ctx);
+    if (ctx->smaa_valid) {                               /* the frame went through the SMAA passes: this is what the reference puts on screen */
+        int rc_ = rtb_sync(ctx);
+        if (rc_) return rc_;
+        CU(cudaMemcpy(dst, ctx->smaa_out, n * 4, cudaMemcpyDeviceToHost));
+        return RTB_OK;
+    }
     if (!ctx->fb8) CU(cudaMalloc(&ctx->fb8, (size_t)ctx->width * ctx->height * 4));
     rgba8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const float4*)(ctx->fb_full ? ctx->fb_full : ctx->fb), (uchar4*)ctx->fb8, n);   /* after the frame, same stream */
     CU(cudaGetLastError());

@@ -59,6 +59,13 @@ struct rtb_ctx {
     cudaEvent_t ev_f0 = nullptr, ev_f1 = nullptr;
     bool frame_timed = false;
     float frame_ms = 0.f;
+
+    /* ---- SMAA post-pass (smaa.cu) ---- */
+    int smaa_preset = -1;                        /* -1 = off (the default here; main.cpp:32 asks for ULTRA = 3) */
+    uint8_t *smaa_color = nullptr, *smaa_edges = nullptr, *smaa_blend = nullptr, *smaa_out = nullptr;   /* RGBA8 / RG8 / RGBA8 / RGBA8 targets */
+    uint8_t *smaa_area = nullptr, *smaa_search = nullptr;                                             /* lookup tables */
+    cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;
+    bool smaa_timed = false, smaa_valid = false; /* smaa_valid: smaa_out holds the post-processed version of the last frame */
 };
 
 int rtb_fail(rtb_ctx* c, int code, const char* fmt, ...);
@@ -71,6 +78,9 @@ int rtb_fail(rtb_ctx* c, int code, const char* fmt, ...);
 /* rtb_api.cu */
 int rtb_do_render(rtb_ctx* ctx, float* target, bool target_global_rows, cudaStream_t st, bool counted, bool timed);
 int rtb_compute_local_rows(int height, int rank, int world, int block_rows);
+/* smaa.cu */
+int rtb_smaa_after_frame(rtb_ctx* ctx, const float* frame, cudaStream_t st);
+void rtb_smaa_release(rtb_ctx* ctx);
 /* rtb_multi.cu */
 int rtb_multi_render(rtb_ctx* root);
 void rtb_multi_release(rtb_ctx* ctx);

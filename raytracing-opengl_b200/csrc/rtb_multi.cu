@@ -140,6 +140,11 @@ int rtb_multi_render(rtb_ctx* ctx) {
         deinterleave_kernel<<<(unsigned)((px + 255) / 256), 256, 0, ctx->stream>>>((const float4*)ctx->fb, (const float4*)ctx->gather_scratch, (float4*)ctx->fb_full, m);
         CU(cudaGetLastError());
     }
+    if (ctx->smaa_preset >= 0) {                          /* the post-pass runs on the assembled frame, on the root */
+        rc = rtb_smaa_after_frame(ctx, ctx->fb_full, ctx->stream);
+        if (rc) return rc;
+        ctx->smaa_valid = true;
+    }
     CU(cudaEventRecord(ctx->ev_f1, ctx->stream));
     ctx->frame_timed = true;
     return RTB_OK;

@@ -15,6 +15,10 @@
 #ifdef RTB_HAVE_STB
 #include <stb_image.h>          /* the reference's own decoder (external_sources/stb_image), GLWrapper.cpp:293,325 */
 #endif
+#ifdef RTB_HAVE_SMAA_TABLES
+#include <AreaTex.h>            /* the reference's own lookup tables, compiled in from where they lie (SMAA_Builder.h:6-7,45-79) */
+#include <SearchTex.h>
+#endif
 
 namespace {
 
@@ -126,6 +130,14 @@ bool GLWrapper::init_window()
 	rtb_set_option(ctx, "strict", env_int("RT_STRICT", 1));
 	rtb_set_option(ctx, "kernel", env_int("RT_KERNEL", 0));
 	if (n_gpus > 1 && rtb_set_option(ctx, "gather", env_int("RT_GATHER", 0))) die(ctx, "RT_GATHER");
+	/* src/GLWrapper.cpp:124-130 + SMAA_Builder: the SMAA render targets, shaders and lookup tables */
+	if (SMAA_enabled && env_int("RT_SMAA", 1)) {
+#ifdef RTB_HAVE_SMAA_TABLES
+		if (rtb_smaa_set_tables(ctx, areaTexBytes, searchTexBytes) || rtb_enable_smaa(ctx, (int)SMAA_preset)) die(ctx, "SMAA");
+#else
+		fprintf(stderr, "SMAA requested but this host was built without the reference's AreaTex.h / SearchTex.h: post-pass off\n");
+#endif
+	}
 	window = rtb_shim_create_window(this, env_int("RT_FRAMES", 1));
 	printf("rtb200 %s, %dx%d\n", rtb_version(), width, height);
 	return true;
@@ -154,11 +166,11 @@ void GLWrapper::stop()
 	if (window) { rtb_shim_destroy_window(window); window = nullptr; }
 }
 
-/* src/GLWrapper.cpp:149-153: the SMAA post-pass is out of scope (BASELINE.json north_star): accepted, ignored */
+/* src/GLWrapper.cpp:149-153 (called before init_window, main.cpp:32-34) */
 void GLWrapper::enable_SMAA(SMAA_PRESET preset)
 {
-	(void)preset;
-	SMAA_enabled = false;
+	SMAA_enabled = true;
+	SMAA_preset = preset;
 }
 
 /* src/GLWrapper.cpp:155-165: glDrawArrays(GL_TRIANGLES, 0, 6) -> one launch of the ray-trace kernel */
@@ -245,6 +257,12 @@ void GLWrapper::present()
 		char name[64];
 		snprintf(name, sizeof name, "/frame_%04d.npy", frame_index);
 		write_npy(dd + name, "<f4", { (size_t)height, (size_t)width, 4 }, px.data(), px.size() * sizeof(float));
+		if (SMAA_enabled && env_int("RT_SMAA", 1)) {           /* what the reference puts on screen: the SMAA-filtered RGBA8 image */
+			std::vector<unsigned char> px8((size_t)width * height * 4);
+			if (rtb_read_rgba8(ctx, px8.data())) die(ctx, "read frame");
+			snprintf(name, sizeof name, "/screen_%04d.npy", frame_index);
+			write_npy(dd + name, "|u1", { (size_t)height, (size_t)width, 4 }, px8.data(), px8.size());
+		}
 	} else {
 		rtb_sync(ctx);
 	}

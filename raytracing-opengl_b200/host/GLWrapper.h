@@ -13,6 +13,8 @@
  *   RT_DUMP_DIR            write frame_NNNN.npy (RGBA32F, row 0 = bottom), the uploaded uniform buffers and the
  *                          decoded textures there
  *   RT_STRICT / RT_KERNEL / RT_DEVICE   rtb_set_option("strict"/"kernel"), CUDA device
+ *   RT_GPUS / RT_GATHER / RT_BLOCK_ROWS all GPUs of the box behind the same draw() (rtb_create_multi)
+ *   RT_SMAA                0 switches the SMAA post-pass off although main.cpp:32 enables it (default 1)
  */
 #pragma once
 
@@ -24,7 +26,7 @@
 #include <cstdio>
 #include <glm/glm.hpp>
 
-enum SMAA_PRESET { LOW, MEDIUM, HIGH, ULTRA };     /* src/SMAA_Builder.h:9-12; SMAA itself is out of scope */
+enum SMAA_PRESET { LOW, MEDIUM, HIGH, ULTRA };     /* src/SMAA_Builder.h:9-12 */
 
 struct rt_defines;
 struct rtb_ctx;
@@ -65,5 +67,6 @@ private:
 	bool fullScreen = true;
 	bool useCustomResolution = false;
 	bool SMAA_enabled = false;
+	SMAA_PRESET SMAA_preset = ULTRA;
 	int frame_index = 0;
 };

@@ -73,3 +73,14 @@ def procedural_textures(cube_size=64, small=True) -> TextureSet:
             a[..., 3] = np.where((x // max(1, w // 16)) % 2 == 0, 255, (x * 200 // w + 30)).astype(np.uint8)
         ts.tex2d[unit] = np.ascontiguousarray(a)
     return ts
+
+
+def smaa_tables():
+    """(AreaTex [560,160,2] uint8, SearchTex [16,64] uint8) from the asset mirror the host Makefile fills from the reference's
+    src/AreaTex.h / src/SearchTex.h (host/build/assets/smaa, git-ignored; the repository ships no copy), or None when absent."""
+    import os
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host", "build", "assets", "smaa")
+    a, s = os.path.join(d, "area_rg8_160x560.bin"), os.path.join(d, "search_r8_64x16.bin")
+    if not (os.path.isfile(a) and os.path.isfile(s)):
+        return None
+    return np.fromfile(a, dtype=np.uint8).reshape(560, 160, 2), np.fromfile(s, dtype=np.uint8).reshape(16, 64)

@@ -1,6 +1,7 @@
 """Properties of the compiled sm_100a code that the measured performance depends on (CPU only: ptxas logs and SASS of the in-tree build).
 Each one guards a regression that was hit while developing:
-  * the quad kernel must fit 4 CTAs x 128 threads per SM (<= 128 registers): at 166 registers the textured default scene ran 30 % slower;
+  * the quad kernel calls its scene scan (one copy of the scan instead of three inlined ones: it was instruction-fetch bound) and must fit
+    3 CTAs x 128 threads per SM (<= 168 registers; forcing 128 registers / 4 CTAs was measured: fused 0.91 -> 0.95 ms on default1080);
   * the persistent kernel runs one 640-thread CTA per SM (<= 96 registers after allocation granularity) and must not spill inside its loops
     more than it does today;
   * the scene is staged with a TMA bulk copy and the solver uses the packed FFMA2 instruction (DESIGN.md sections 3 and 4)."""
@@ -30,7 +31,8 @@ def _ptxas(log, entry):
 def test_register_budgets_of_the_two_kernels(log):
     for counted in ("Lb0", "Lb1"):
         regs, st, ld = _ptxas(log, "quad_kernelI" + counted)
-        assert regs <= 128, f"quad_kernel<{counted}> uses {regs} registers: fewer than 4 CTAs of 128 threads fit an SM"
+        if counted == "Lb0":                                 # (the counting variant is an untimed instrumentation build)
+            assert regs <= 168, f"quad_kernel<{counted}> uses {regs} registers: fewer than 3 CTAs of 128 threads fit an SM"
         assert st <= 128 and ld <= 128, (st, ld)
         regs, st, ld = _ptxas(log, "persistent_kernelI" + counted)
         assert regs <= 96, f"persistent_kernel<{counted}> uses {regs} registers: a 640-thread CTA no longer fits"

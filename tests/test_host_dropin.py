@@ -126,3 +126,26 @@ def test_unchanged_frame_loop_animates_and_reuploads_every_frame():
                         tex2d={u: np.load(os.path.join(td, f"tex_{u}.npy")) for u in range(1, 6)})
         err = pixel_err(frames[2], Oracle(sc, ts).render())
         assert err.max() <= 1e-4, (float(err.max()), int((err > 1e-4).sum()))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isfile(BIN), reason="rt_headless did not travel (built only where /root/reference exists)")
+def test_unchanged_main_cpp_gets_its_smaa_post_pass():
+    """main.cpp:32 calls enable_SMAA(ULTRA) before init_window(): what the drop-in puts "on screen" is the ray-traced frame after
+    the reference's three SMAA passes (GLWrapper.cpp:173-204) — checked against the reference's own SMAA.h compiled as C++."""
+    from oracle.smaa_binding import PRESETS, have_smaa_ref, smaa_ref
+    if not have_smaa_ref():
+        pytest.skip("oracle/_ref/libsmaa_ref.so did not travel")
+    with tempfile.TemporaryDirectory() as td:
+        env = dict(os.environ, RT_WIDTH="320", RT_HEIGHT="180", RT_ITERATIONS="3", RT_FRAMES="1", RT_DUMP_DIR=td, RT_STRICT="1")
+        r = subprocess.run([BIN], capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        frame = np.load(os.path.join(td, "frame_0000.npy"))
+        screen = np.load(os.path.join(td, "screen_0000.npy"))
+        raw8 = (np.clip(frame, 0, 1) * 255.0 + 0.5).astype(np.uint8)
+        want, _, _ = smaa_ref(raw8, PRESETS["ULTRA"])
+        assert np.array_equal(screen, want)
+        assert (screen != raw8).any()
+        env["RT_SMAA"] = "0"                                          # the headless switch
+        r = subprocess.run([BIN], capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0 and not os.path.isfile(os.path.join(td, "screen_0001.npy"))
