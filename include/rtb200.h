@@ -141,7 +141,9 @@ int rtb_set_texture2d(rtb_ctx* ctx, int unit, const uint8_t* pixels, int w, int 
  * reciprocals, rotation matrices — 1.6x faster, parity by the envelope criterion);
  * "cull" (1 = conservative bounding-sphere reject before the torus solve; result-preserving, reported separately from
  * the roofline); "ctas_per_sm" (quad kernel); "coop" (0 = switch the persistent kernel's cooperative drain off: an A/B
- * and test switch, results are identical); "gather" (enum rtb_gather_mode, multi-GPU contexts). */
+ * and test switch, results are identical); "gather" (enum rtb_gather_mode, multi-GPU contexts); "smaa_compact" (0 = run
+ * SMAA's blending-weight pass over every pixel as the reference draws it instead of over the compacted edge pixels: an
+ * A/B and test switch, results are identical). */
 int rtb_set_option(rtb_ctx* ctx, const char* key, int value);
 
 /* GLWrapper::draw()  (GLWrapper.h:34; GLWrapper.cpp:155-165): render one frame

@@ -451,6 +451,7 @@ int rtb_set_option(rtb_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "cull")) ctx->opt_cull = value ? 1 : 0;
     else if (!strcmp(key, "ctas_per_sm")) ctx->opt_ctas_per_sm = value;
     else if (!strcmp(key, "coop")) ctx->opt_coop = value ? 1 : 0;
+    else if (!strcmp(key, "smaa_compact")) ctx->opt_smaa_compact = value ? 1 : 0;
     else if (!strcmp(key, "gather")) { if (value != RTB_GATHER_NCCL && value != RTB_GATHER_P2P) return fail(ctx, RTB_ERR_INVALID, "gather must be 0 (NCCL) or 1 (P2P)");
         if (value == RTB_GATHER_P2P && (ctx->peers.empty() || !ctx->p2p_ok)) return fail(ctx, RTB_ERR_STATE, "P2P gather needs a multi-device context whose GPUs have peer access to device 0");
         ctx->opt_gather = value; }

@@ -64,6 +64,9 @@ struct rtb_ctx {
     int smaa_preset = -1;                        /* -1 = off (the default here; main.cpp:32 asks for ULTRA = 3) */
     uint8_t *smaa_color = nullptr, *smaa_edges = nullptr, *smaa_blend = nullptr, *smaa_out = nullptr;   /* RGBA8 / RG8 / RGBA8 / RGBA8 targets */
     uint8_t *smaa_area = nullptr, *smaa_search = nullptr;                                             /* lookup tables */
+    float* smaa_uv = nullptr;                    /* texel-centre coordinates per column / row */
+    unsigned *smaa_list = nullptr, *smaa_count = nullptr;                                             /* pass 2: compacted edge pixels */
+    int opt_smaa_compact = 1;                    /* 0: pass 2 as one full-screen kernel (A/B partner) */
     cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;
     bool smaa_timed = false, smaa_valid = false; /* smaa_valid: smaa_out holds the post-processed version of the last frame */
 };

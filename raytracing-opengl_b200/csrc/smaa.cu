@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 
 #include "rtb_ctx.h"
 
@@ -28,6 +30,10 @@ struct SmaaParams {
     uchar4* out;              /* RGBA8 [h][w] */
     const uchar2* area;       /* RG8 160 x 560 */
     const unsigned char* search;   /* R8 64 x 16 */
+    unsigned* edge_list;      /* pass 2: indices of the pixels whose edges fetch is not zero */
+    unsigned* edge_count;
+    const float* uv;          /* texel-centre coordinates: u[x] = (x + 0.5) / w for x < w, then v[y] = (y + 0.5) / h (the vertex stage's
+                                 interpolated texcoord; one IEEE division per column / row instead of two per pixel and pass) */
     int w, h;
     float rt_x, rt_y, rt_z, rt_w;  /* SMAA_RT_METRICS = (1/W, 1/H, W, H), SMAA_Builder.h:33-35 */
     float threshold;          /* presets, SMAA.h:304-324 */
@@ -37,12 +43,21 @@ struct SmaaParams {
 constexpr int AREA_W = 160, AREA_H = 560, SEARCH_W = 64, SEARCH_H = 16;
 constexpr float AREATEX_MAX_DISTANCE = 16.f, AREATEX_MAX_DISTANCE_DIAG = 20.f, AREATEX_SUBTEX_SIZE = 1.0f / 7.0f;
 
-__device__ __forceinline__ float u2f(unsigned char v) { return (float)v / 255.0f; }
+/* unorm8 -> float: v / 255.0f, correctly rounded, without the division: one product and one Markstein correction (two FFMA —
+ * explicit fmaf() is not a contraction, so -fmad=false leaves it alone).  Equal to the IEEE quotient for all 256 inputs
+ * (tests/test_smaa.py::test_unorm8_decode_is_the_ieee_quotient runs the same sequence on the CPU). */
+__device__ __forceinline__ float u2f(unsigned char v) {
+    /* (float)v without the conversion unit (the XU pipe ran at 60-70 % in these passes): 2^23 + v is exact in fp32 */
+    const float x = __uint_as_float(0x4B000000u | (unsigned)v) - 8388608.0f, rcp = 1.0f / 255.0f;
+    const float q = x * rcp;
+    return fmaf(fmaf(-q, 255.0f, x), rcp, q);
+}
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 __device__ __forceinline__ unsigned char unorm8(float v) {
     v = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
     if (!(v == v)) v = 0.f;
-    return (unsigned char)(v * 255.0f + 0.5f);
+    /* (unsigned char)(v * 255 + 0.5) without the conversion unit: RD(t + 2^23) = floor(t) + 2^23 for t in [0.5, 255.5] */
+    return (unsigned char)(__float_as_uint(__fadd_rd(v * 255.0f + 0.5f, 8388608.0f)) & 0xffu);
 }
 
 /* ---- the sampler: LINEAR + CLAMP_TO_EDGE on unorm8 texels, one template per texel type ---- */
@@ -62,8 +77,11 @@ __device__ __forceinline__ float texel1(const unsigned char* t, int w, int h, in
 struct Footprint { int x0, y0; float ax, ay; };
 __device__ __forceinline__ Footprint footprint(float u, float v, int w, int h) {
     const float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
-    const float fx = floorf(x), fy = floorf(y);
-    return { (int)fx, (int)fy, x - fx, y - fy };
+    /* floor() and the conversion to int through one round-down add (FMA pipe instead of two XU instructions): for
+     * |x| < 2^22, RD(x + 1.5 * 2^23) = floor(x) + 1.5 * 2^23 exactly, with the integer in the low mantissa bits */
+    const float tx = __fadd_rd(x, 12582912.0f), ty = __fadd_rd(y, 12582912.0f);
+    const float fx = tx - 12582912.0f, fy = ty - 12582912.0f;
+    return { __float_as_int(tx) - 0x4B400000, __float_as_int(ty) - 0x4B400000, x - fx, y - fy };
 }
 /* (a (1 - t) + b t): with t == 0 this is a exactly, whatever b is — the fetch of b is skipped then */
 #define LERP1(a, b, t) ((a) * (1.0f - (t)) + (b) * (t))
@@ -106,7 +124,7 @@ __device__ __forceinline__ float luma(const SmaaParams& P, float u, float v) {
 __global__ void smaa_edge_kernel(const SmaaParams P) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= P.w || y >= P.h) return;
-    const float u = ((float)x + 0.5f) / (float)P.w, v = ((float)y + 0.5f) / (float)P.h;
+    const float u = __ldg(P.uv + x), v = __ldg(P.uv + P.w + y);
     /* neighbour coordinates as the vertex stage forms them (SMAA.h:645-650): metrics * offset + texcoord */
     const float ul = P.rt_x * -1.0f + u, vt = P.rt_y * -1.0f + v, ur = P.rt_x * 1.0f + u, vb = P.rt_y * 1.0f + v;
     const float ull = P.rt_x * -2.0f + u, vtt = P.rt_y * -2.0f + v;
@@ -129,33 +147,45 @@ __global__ void smaa_edge_kernel(const SmaaParams P) {
 }
 
 /* ------------------------------------------------------------------ pass 2: blending weights, SMAA.h:836-1247 */
-__device__ __forceinline__ F2 edges_at(const SmaaParams& P, float u, float v) { return sample2(P.edges, P.w, P.h, u, v); }
+/* pass 2 fetches edges at ~40 places: one out-of-line copy of the sampler keeps the kernel inside the instruction cache
+ * (inlined everywhere it was 4 000 instructions and stalled on instruction fetch 12 warps per issue) */
+#ifndef SMAA_EDGES_INLINE
+#define SMAA_EDGES_INLINE 0
+#endif
+#if SMAA_EDGES_INLINE
+#define SMAA_P2_INLINE __forceinline__
+#else
+#define SMAA_P2_INLINE __noinline__
+#endif
+__device__ SMAA_P2_INLINE F2 edges_at(const SmaaParams& P, float u, float v) { return sample2(P.edges, P.w, P.h, u, v); }
 __device__ __forceinline__ F2 edges_off(const SmaaParams& P, float u, float v, int ox, int oy) {      /* textureLodOffset */
-    return sample2(P.edges, P.w, P.h, u + (float)ox * P.rt_x, v + (float)oy * P.rt_y);
+    return edges_at(P, u + (float)ox * P.rt_x, v + (float)oy * P.rt_y);
 }
+__device__ SMAA_P2_INLINE F2 area_at(const SmaaParams& P, float u, float v) { return sample2(P.area, AREA_W, AREA_H, u, v); }
 /* two binary values out of one bilinear fetch at a quarter-pixel offset, SMAA.h:836-858 */
 __device__ __forceinline__ float decode_r(float r) { return roundh(r * fabsf(5.0f * r - 5.0f * 0.75f)); }
 
-/* diagonal searches, SMAA.h:862-892: returns (steps, last weight); e = the last edges fetched */
-__device__ F2 search_diag1(const SmaaParams& P, float u, float v, float dirx, float diry, F2& e) {
-    float cx = u, cy = v, cz = -1.0f, cw = 1.0f;
-    while (cz < (float)(P.max_steps_diag - 1) && cw > 0.9f) {
+/* diagonal searches, SMAA.h:862-892: returns (steps, last weight); e = the last edges fetched.
+ * (Fetching several steps ahead — the coordinates do not depend on what was fetched — was measured and is slower: 0.38 / 0.43 /
+ * 0.49 / 0.57 ms per 4K frame for 1 / 2 / 4 / 8 steps at once.  The pass is bound by instruction issue and fetch, not by the
+ * memory round trips.) */
+template <bool DECODE>
+__device__ F2 search_diag(const SmaaParams& P, float cx, float cy, float dirx, float diry, F2& e) {
+    float cz = -1.0f, cw = 1.0f;
+    const float last = (float)(P.max_steps_diag - 1);
+    while (cz < last && cw > 0.9f) {
         cx = P.rt_x * dirx + cx; cy = P.rt_y * diry + cy; cz = 1.0f * 1.0f + cz;
         e = edges_at(P, cx, cy);
+        if (DECODE) e = { decode_r(e.x), roundh(e.y) };
         cw = e.x * 0.5f + e.y * 0.5f;
     }
     return { cz, cw };
 }
-__device__ F2 search_diag2(const SmaaParams& P, float u, float v, float dirx, float diry, F2& e) {
-    float cx = u, cy = v, cz = -1.0f, cw = 1.0f;
-    cx += 0.25f * P.rt_x;
-    while (cz < (float)(P.max_steps_diag - 1) && cw > 0.9f) {
-        cx = P.rt_x * dirx + cx; cy = P.rt_y * diry + cy; cz = 1.0f * 1.0f + cz;
-        e = edges_at(P, cx, cy);
-        e = { decode_r(e.x), roundh(e.y) };
-        cw = e.x * 0.5f + e.y * 0.5f;
-    }
-    return { cz, cw };
+__device__ __forceinline__ F2 search_diag1(const SmaaParams& P, float u, float v, float dirx, float diry, F2& e) {
+    return search_diag<false>(P, u, v, dirx, diry, e);
+}
+__device__ __forceinline__ F2 search_diag2(const SmaaParams& P, float u, float v, float dirx, float diry, F2& e) {
+    return search_diag<true>(P, u + 0.25f * P.rt_x, v, dirx, diry, e);
 }
 __device__ __forceinline__ F2 area_diag(const SmaaParams& P, float distx, float disty, float ex, float ey, float offset) {   /* SMAA.h:900-914 */
     float tx = AREATEX_MAX_DISTANCE_DIAG * ex + distx, ty = AREATEX_MAX_DISTANCE_DIAG * ey + disty;
@@ -163,7 +193,7 @@ __device__ __forceinline__ F2 area_diag(const SmaaParams& P, float distx, float 
     tx = psx * tx + 0.5f * psx; ty = psy * ty + 0.5f * psy;
     tx += 0.5f;
     ty += AREATEX_SUBTEX_SIZE * offset;
-    return sample2(P.area, AREA_W, AREA_H, tx, ty);
+    return area_at(P, tx, ty);
 }
 __device__ F2 diag_weights(const SmaaParams& P, float u, float v, F2 e) {                       /* SMAA.h:919-989, subsampleIndices = 0 */
     F2 weights = { 0.f, 0.f };
@@ -212,28 +242,43 @@ __device__ __forceinline__ float search_length(const SmaaParams& P, float ex, fl
     sx *= 1.0f / 64.0f; sy *= 1.0f / 16.0f; bx *= 1.0f / 64.0f; by *= 1.0f / 16.0f;
     return sample1(P.search, SEARCH_W, SEARCH_H, sx * ex + bx, sy * ey + by);
 }
-/* the four axis searches, SMAA.h:1019-1085: two pixels per step through one bilinear fetch between them */
+/* the four axis searches, SMAA.h:1019-1085: two pixels per step through one bilinear fetch between them.
+ * HORZ: walks u (else v); NEG: towards smaller coordinates.  Returns the coordinate after the last accepted step and the
+ * edges fetched there. */
+template <bool HORZ, bool NEG>
+__device__ float search_axis(const SmaaParams& P, float u, float v, float end, F2& e) {
+    const float step = NEG ? -2.0f : 2.0f;
+    e = HORZ ? F2{ 0.f, 1.f } : F2{ 1.f, 0.f };
+    for (;;) {
+        const float pos = HORZ ? u : v, along = HORZ ? e.y : e.x, across = HORZ ? e.x : e.y;
+        if (!((NEG ? pos > end : pos < end) && along > 0.8281f && across == 0.0f)) return pos;
+        e = edges_at(P, u, v);
+        /* texcoord = mad((-2, -0) or (0, 2) ..., metrics, texcoord): the zero product is a signed zero and c + (+-0) = c */
+        if (HORZ) u = step * P.rt_x + u;
+        else v = step * P.rt_y + v;
+    }
+}
 __device__ float search_x_left(const SmaaParams& P, float u, float v, float end) {
-    F2 e = { 0.f, 1.f };
-    while (u > end && e.y > 0.8281f && e.x == 0.0f) { e = edges_at(P, u, v); u = -2.0f * P.rt_x + u; v = -0.0f * P.rt_y + v; }
+    F2 e;
+    u = search_axis<true, true>(P, u, v, end, e);
     const float offset = -(255.0f / 127.0f) * search_length(P, e.x, e.y, 0.0f) + 3.25f;
     return P.rt_x * offset + u;
 }
 __device__ float search_x_right(const SmaaParams& P, float u, float v, float end) {
-    F2 e = { 0.f, 1.f };
-    while (u < end && e.y > 0.8281f && e.x == 0.0f) { e = edges_at(P, u, v); u = 2.0f * P.rt_x + u; v = 0.0f * P.rt_y + v; }
+    F2 e;
+    u = search_axis<true, false>(P, u, v, end, e);
     const float offset = -(255.0f / 127.0f) * search_length(P, e.x, e.y, 0.5f) + 3.25f;
     return -P.rt_x * offset + u;
 }
 __device__ float search_y_up(const SmaaParams& P, float u, float v, float end) {
-    F2 e = { 1.f, 0.f };
-    while (v > end && e.x > 0.8281f && e.y == 0.0f) { e = edges_at(P, u, v); u = -0.0f * P.rt_x + u; v = -2.0f * P.rt_y + v; }
+    F2 e;
+    v = search_axis<false, true>(P, u, v, end, e);
     const float offset = -(255.0f / 127.0f) * search_length(P, e.y, e.x, 0.0f) + 3.25f;
     return P.rt_y * offset + v;
 }
 __device__ float search_y_down(const SmaaParams& P, float u, float v, float end) {
-    F2 e = { 1.f, 0.f };
-    while (v < end && e.x > 0.8281f && e.y == 0.0f) { e = edges_at(P, u, v); u = 0.0f * P.rt_x + u; v = 2.0f * P.rt_y + v; }
+    F2 e;
+    v = search_axis<false, false>(P, u, v, end, e);
     const float offset = -(255.0f / 127.0f) * search_length(P, e.y, e.x, 0.5f) + 3.25f;
     return -P.rt_y * offset + v;
 }
@@ -242,7 +287,7 @@ __device__ __forceinline__ F2 area(const SmaaParams& P, float distx, float disty
     const float psx = 1.0f / 160.0f, psy = 1.0f / 560.0f;
     tx = psx * tx + 0.5f * psx; ty = psy * ty + 0.5f * psy;
     ty = AREATEX_SUBTEX_SIZE * offset + ty;
-    return sample2(P.area, AREA_W, AREA_H, tx, ty);
+    return area_at(P, tx, ty);
 }
 /* corner patterns, SMAA.h:1108-1140: which == 0 horizontal (red edges above / below), 1 vertical (green edges left / right) */
 __device__ __forceinline__ void corner_pattern(const SmaaParams& P, int which, F2& weights, float c0x, float c0y, float c1x, float c1y, float dx, float dy) {
@@ -266,65 +311,121 @@ __device__ __forceinline__ void corner_pattern(const SmaaParams& P, int which, F
     }
     weights.x *= sat(fx); weights.y *= sat(fy);
 }
+/* the pixel shader body of pass 2 for one pixel whose edges fetch `e` is not zero (SMAA.h:1145-1247) */
+__device__ uchar4 blend_weights(const SmaaParams& P, int x, int y, F2 e) {
+    const float u = __ldg(P.uv + x), v = __ldg(P.uv + P.w + y);
+    F4 wgt = { 0.f, 0.f, 0.f, 0.f };
+    /* the vertex stage's offsets, SMAA.h:655-668 */
+    const float pixx = u * P.rt_z, pixy = v * P.rt_w;
+    const float o0x = P.rt_x * -0.25f + u, o0y = P.rt_y * -0.125f + v, o0z = P.rt_x * 1.25f + u, o0w = P.rt_y * -0.125f + v;
+    const float o1x = P.rt_x * -0.125f + u, o1y = P.rt_y * -0.25f + v, o1z = P.rt_x * -0.125f + u, o1w = P.rt_y * 1.25f + v;
+    const float ms = (float)P.max_steps;
+    const float o2x = P.rt_x * (-2.0f * ms) + o0x, o2y = P.rt_x * (2.0f * ms) + o0z, o2z = P.rt_y * (-2.0f * ms) + o1y, o2w = P.rt_y * (2.0f * ms) + o1w;
+    if (e.y > 0.0f) {                                                /* edge at north */
+        bool axis = true;
+        if (P.max_steps_diag > 0) {
+            const F2 dw = diag_weights(P, u, v, e);
+            wgt.x = dw.x; wgt.y = dw.y;
+            axis = wgt.x == -wgt.y;                                  /* no diagonal found: horizontal / vertical processing */
+        }
+        if (axis) {
+            const float cx = search_x_left(P, o0x, o0y, o2x), cy = o1y;
+            float dx = cx;
+            const float e1 = edges_at(P, cx, cy).x;
+            const float cz = search_x_right(P, o0z, o0w, o2y);
+            float dy = cz;
+            dx = fabsf(roundh(P.rt_z * dx + -pixx)); dy = fabsf(roundh(P.rt_z * dy + -pixx));
+            const float sdx = sqrtf(dx), sdy = sqrtf(dy);
+            const float e2 = edges_off(P, cz, cy, 1, 0).x;
+            F2 w2 = area(P, sdx, sdy, e1, e2, 0.f);
+            corner_pattern(P, 0, w2, cx, v, cz, v, dx, dy);
+            wgt.x = w2.x; wgt.y = w2.y;
+        } else {
+            e.x = 0.0f;                                              /* a diagonal was found: skip vertical processing */
+        }
+    }
+    if (e.x > 0.0f) {                                                /* edge at west */
+        const float cy = search_y_up(P, o1x, o1y, o2z), cx = o0x;
+        float dx = cy;
+        const float e1 = edges_at(P, cx, cy).y;
+        const float cz = search_y_down(P, o1z, o1w, o2w);
+        float dy = cz;
+        dx = fabsf(roundh(P.rt_w * dx + -pixy)); dy = fabsf(roundh(P.rt_w * dy + -pixy));
+        const float sdx = sqrtf(dx), sdy = sqrtf(dy);
+        const float e2 = edges_off(P, cx, cz, 0, 1).y;
+        F2 w2 = area(P, sdx, sdy, e1, e2, 0.f);
+        corner_pattern(P, 1, w2, u, cy, u, cz, dx, dy);
+        wgt.z = w2.x; wgt.w = w2.y;
+    }
+    return make_uchar4(unorm8(wgt.x), unorm8(wgt.y), unorm8(wgt.z), unorm8(wgt.w));
+}
+/* pass 2 as the reference draws it: every pixel runs the shader, the few edge pixels with their divergent searches
+ * (option "smaa_compact" = 0; kept as the A/B partner and cross-check of the two kernels below) */
 __global__ void smaa_blend_kernel(const SmaaParams P) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= P.w || y >= P.h) return;
-    const float u = ((float)x + 0.5f) / (float)P.w, v = ((float)y + 0.5f) / (float)P.h;
-    F2 e = edges_at(P, u, v);
-    F4 wgt = { 0.f, 0.f, 0.f, 0.f };
-    if (e.x > 0.f || e.y > 0.f) {
-        /* the vertex stage's offsets, SMAA.h:655-668 */
-        const float pixx = u * P.rt_z, pixy = v * P.rt_w;
-        const float o0x = P.rt_x * -0.25f + u, o0y = P.rt_y * -0.125f + v, o0z = P.rt_x * 1.25f + u, o0w = P.rt_y * -0.125f + v;
-        const float o1x = P.rt_x * -0.125f + u, o1y = P.rt_y * -0.25f + v, o1z = P.rt_x * -0.125f + u, o1w = P.rt_y * 1.25f + v;
-        const float ms = (float)P.max_steps;
-        const float o2x = P.rt_x * (-2.0f * ms) + o0x, o2y = P.rt_x * (2.0f * ms) + o0z, o2z = P.rt_y * (-2.0f * ms) + o1y, o2w = P.rt_y * (2.0f * ms) + o1w;
-        if (e.y > 0.0f) {                                            /* edge at north */
-            bool axis = true;
-            if (P.max_steps_diag > 0) {
-                const F2 dw = diag_weights(P, u, v, e);
-                wgt.x = dw.x; wgt.y = dw.y;
-                axis = wgt.x == -wgt.y;                              /* no diagonal found: horizontal / vertical processing */
-            }
-            if (axis) {
-                const float cx = search_x_left(P, o0x, o0y, o2x), cy = o1y;
-                float dx = cx;
-                const float e1 = edges_at(P, cx, cy).x;
-                const float cz = search_x_right(P, o0z, o0w, o2y);
-                float dy = cz;
-                dx = fabsf(roundh(P.rt_z * dx + -pixx)); dy = fabsf(roundh(P.rt_z * dy + -pixx));
-                const float sdx = sqrtf(dx), sdy = sqrtf(dy);
-                const float e2 = edges_off(P, cz, cy, 1, 0).x;
-                F2 w2 = area(P, sdx, sdy, e1, e2, 0.f);
-                corner_pattern(P, 0, w2, cx, v, cz, v, dx, dy);
-                wgt.x = w2.x; wgt.y = w2.y;
-            } else {
-                e.x = 0.0f;                                          /* a diagonal was found: skip vertical processing */
-            }
-        }
-        if (e.x > 0.0f) {                                            /* edge at west */
-            const float cy = search_y_up(P, o1x, o1y, o2z), cx = o0x;
-            float dx = cy;
-            const float e1 = edges_at(P, cx, cy).y;
-            const float cz = search_y_down(P, o1z, o1w, o2w);
-            float dy = cz;
-            dx = fabsf(roundh(P.rt_w * dx + -pixy)); dy = fabsf(roundh(P.rt_w * dy + -pixy));
-            const float sdx = sqrtf(dx), sdy = sqrtf(dy);
-            const float e2 = edges_off(P, cx, cz, 0, 1).y;
-            F2 w2 = area(P, sdx, sdy, e1, e2, 0.f);
-            corner_pattern(P, 1, w2, u, cy, u, cz, dx, dy);
-            wgt.z = w2.x; wgt.w = w2.y;
+    const float u = __ldg(P.uv + x), v = __ldg(P.uv + P.w + y);
+    const F2 e = edges_at(P, u, v);
+    uchar4 o = make_uchar4(0, 0, 0, 0);
+    if (e.x > 0.f || e.y > 0.f) o = blend_weights(P, x, y, e);
+    P.blend[(size_t)y * P.w + x] = o;
+}
+/* pass 2, compacted (the default).  2a streams: every pixel evaluates the shader's own predicate (its edges fetch — which, at
+ * the quarter-ulp the coordinate arithmetic is off a texel centre, may pick up a neighbour's edge), stores the zero weights
+ * of a non-edge pixel and appends an edge pixel to a list (one atomic per warp).  2b runs the searches with every lane on an
+ * edge pixel: the latency chains of up to ~200 dependent fetches no longer hold 31 idle lanes each. */
+constexpr int CLASSIFY_ROWS = 4;                                     /* rows per thread: four independent fetches in flight */
+__global__ void smaa_classify_kernel(const SmaaParams P) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
+    bool edge[CLASSIFY_ROWS];
+    int ys[CLASSIFY_ROWS];
+#pragma unroll
+    for (int k = 0; k < CLASSIFY_ROWS; k++) {
+        const int y = ys[k] = (blockIdx.y * CLASSIFY_ROWS + k) * blockDim.y + threadIdx.y;
+        edge[k] = false;
+        if (x < P.w && y < P.h) {
+            const float u = __ldg(P.uv + x), v = __ldg(P.uv + P.w + y);
+            const F2 e = sample2(P.edges, P.w, P.h, u, v);
+            edge[k] = e.x > 0.f || e.y > 0.f;
+            if (!edge[k]) P.blend[(size_t)y * P.w + x] = make_uchar4(0, 0, 0, 0);
         }
     }
-    P.blend[(size_t)y * P.w + x] = make_uchar4(unorm8(wgt.x), unorm8(wgt.y), unorm8(wgt.z), unorm8(wgt.w));
+#pragma unroll
+    for (int k = 0; k < CLASSIFY_ROWS; k++) {
+        const unsigned m = __ballot_sync(0xffffffffu, edge[k]);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(P.edge_count, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (edge[k]) P.edge_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)ys[k] * (unsigned)P.w + (unsigned)x;
+        }
+    }
+}
+__global__ void smaa_uv_kernel(float* uv, int w, int h) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w) uv[i] = ((float)i + 0.5f) / (float)w;
+    else if (i < w + h) uv[i] = ((float)(i - w) + 0.5f) / (float)h;
+}
+__global__ void __launch_bounds__(128) smaa_blend_list_kernel(const SmaaParams P) {
+    const unsigned n = *P.edge_count;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned idx = P.edge_list[i];
+        const int y = (int)(idx / (unsigned)P.w), x = (int)(idx - (unsigned)y * (unsigned)P.w);
+        const float u = __ldg(P.uv + x), v = __ldg(P.uv + P.w + y);
+        P.blend[idx] = blend_weights(P, x, y, edges_at(P, u, v));
+    }
 }
 
 /* ------------------------------------------------------------------ pass 3: neighbourhood blending, SMAA.h:1252-1308 */
 __global__ void smaa_neighborhood_kernel(const SmaaParams P) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= P.w || y >= P.h) return;
-    const float u = ((float)x + 0.5f) / (float)P.w, v = ((float)y + 0.5f) / (float)P.h;
-    const float ox = P.rt_x * 1.0f + u, oy = P.rt_y * 0.0f + v, oz = P.rt_x * 0.0f + u, ow = P.rt_y * 1.0f + v;
+    const float u = __ldg(P.uv + x), v = __ldg(P.uv + P.w + y);
+    /* offset = mad(metrics.xyxy, (1, 0, 0, 1), texcoord.xyxy): the two zero products are +0 (the metrics are positive and
+     * finite) and +0 + c = c for the positive coordinates, so .y and .z are v and u themselves — which lets the three fetches
+     * at this pixel's own column / row share their footprints */
+    const float ox = P.rt_x * 1.0f + u, oy = v, oz = u, ow = P.rt_y * 1.0f + v;
     const float ax = sample4(P.blend, P.w, P.h, ox, oy).w;           /* right  */
     const float ay = sample4(P.blend, P.w, P.h, oz, ow).y;           /* top    */
     const F4 self = sample4(P.blend, P.w, P.h, u, v);
@@ -374,12 +475,25 @@ int rtb_smaa_run(rtb_ctx* ctx, cudaStream_t st) {
     if (!ctx->smaa_area || !ctx->smaa_search) return rtb_fail(ctx, RTB_ERR_STATE, "SMAA is enabled but the area / search tables were never set (rtb_smaa_set_tables)");
     P.color = (const uchar4*)ctx->smaa_color; P.edges = (uchar2*)ctx->smaa_edges; P.blend = (uchar4*)ctx->smaa_blend; P.out = (uchar4*)ctx->smaa_out;
     P.area = (const uchar2*)ctx->smaa_area; P.search = ctx->smaa_search;
+    P.edge_list = nullptr; P.edge_count = nullptr; P.uv = ctx->smaa_uv;
     P.w = ctx->width; P.h = ctx->height;
     P.rt_x = 1.0f / (float)P.w; P.rt_y = 1.0f / (float)P.h; P.rt_z = (float)P.w; P.rt_w = (float)P.h;
-    const dim3 block(32, 8), grid((P.w + 31) / 32, (P.h + 7) / 8);
+    dim3 block(32, 8);
+    if (const char* e = getenv("RTB_SMAA_BLOCK")) {                      /* development: "WxH", W a multiple of 32 (one warp = one row segment) */
+        int bw = 0, bh = 0;
+        if (sscanf(e, "%dx%d", &bw, &bh) == 2 && bw >= 32 && bw % 32 == 0 && bh >= 1 && bw * bh <= 1024) block = dim3(bw, bh);
+    }
+    const dim3 grid((P.w + block.x - 1) / block.x, (P.h + block.y - 1) / block.y);
     if (ctx->smaa_timed) CU(cudaEventRecord(ctx->ev_s0, st));
     smaa_edge_kernel<<<grid, block, 0, st>>>(P);
-    smaa_blend_kernel<<<grid, block, 0, st>>>(P);
+    if (ctx->opt_smaa_compact) {
+        P.edge_list = ctx->smaa_list; P.edge_count = ctx->smaa_count;
+        CU(cudaMemsetAsync(ctx->smaa_count, 0, sizeof(unsigned), st));
+        smaa_classify_kernel<<<dim3(grid.x, (P.h + block.y * CLASSIFY_ROWS - 1) / (block.y * CLASSIFY_ROWS)), block, 0, st>>>(P);
+        smaa_blend_list_kernel<<<ctx->n_sm * 8, 128, 0, st>>>(P);
+    } else {
+        smaa_blend_kernel<<<grid, block, 0, st>>>(P);
+    }
     smaa_neighborhood_kernel<<<grid, block, 0, st>>>(P);
     CU(cudaGetLastError());
     if (ctx->smaa_timed) CU(cudaEventRecord(ctx->ev_s1, st));
@@ -390,6 +504,14 @@ int rtb_smaa_alloc(rtb_ctx* ctx) {
     const size_t px = (size_t)ctx->width * ctx->height;
     if (!ctx->smaa_color) CU(cudaMalloc(&ctx->smaa_color, px * 4));
     if (!ctx->smaa_edges) CU(cudaMalloc(&ctx->smaa_edges, px * 2));
+    if (!ctx->smaa_list) CU(cudaMalloc(&ctx->smaa_list, px * sizeof(unsigned)));
+    if (!ctx->smaa_count) CU(cudaMalloc(&ctx->smaa_count, sizeof(unsigned)));
+    if (!ctx->smaa_uv) {
+        CU(cudaMalloc(&ctx->smaa_uv, (size_t)(ctx->width + ctx->height) * sizeof(float)));
+        smaa_uv_kernel<<<(ctx->width + ctx->height + 255) / 256, 256, 0, ctx->stream>>>(ctx->smaa_uv, ctx->width, ctx->height);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ctx->stream));      /* the passes may run on a caller's stream */
+    }
     if (!ctx->smaa_blend) CU(cudaMalloc(&ctx->smaa_blend, px * 4));
     if (!ctx->smaa_out) CU(cudaMalloc(&ctx->smaa_out, px * 4));
     if (!ctx->ev_s0) { CU(cudaEventCreate(&ctx->ev_s0)); CU(cudaEventCreate(&ctx->ev_s1)); }
@@ -409,6 +531,8 @@ int rtb_smaa_after_frame(rtb_ctx* ctx, const float* frame, cudaStream_t st) {
 
 void rtb_smaa_release(rtb_ctx* ctx) {
     for (uint8_t** p : { &ctx->smaa_color, &ctx->smaa_edges, &ctx->smaa_blend, &ctx->smaa_out, &ctx->smaa_area, &ctx->smaa_search }) { if (*p) cudaFree(*p); *p = nullptr; }
+    for (unsigned** p : { &ctx->smaa_list, &ctx->smaa_count }) { if (*p) cudaFree(*p); *p = nullptr; }
+    if (ctx->smaa_uv) { cudaFree(ctx->smaa_uv); ctx->smaa_uv = nullptr; }
     if (ctx->ev_s0) { cudaEventDestroy(ctx->ev_s0); cudaEventDestroy(ctx->ev_s1); ctx->ev_s0 = ctx->ev_s1 = nullptr; }
 }
 

@@ -54,6 +54,24 @@ def test_tables_have_the_documented_shapes():
     assert area.shape == (560, 160, 2) and search.shape == (16, 64)   # AreaTex.h:33-34, SearchTex.h:33-34
 
 
+def test_unorm8_decode_is_the_ieee_quotient():
+    """csrc/smaa.cu u2f(): q = v * (1/255); q + fma(-q, 255, v) * (1/255) equals the IEEE quotient v / 255.0f for every byte
+    (the kernels decode texels with it instead of a division; the compiled reference divides)."""
+    import ctypes, ctypes.util
+    libm = ctypes.CDLL(ctypes.util.find_library("m"))
+    libm.fmaf.restype = ctypes.c_float
+    libm.fmaf.argtypes = [ctypes.c_float] * 3
+    rcp = np.float32(1.0) / np.float32(255.0)
+    plain_differs = 0
+    for v in range(256):
+        x = np.float32(v)
+        q = np.float32(x * rcp)
+        got = np.float32(libm.fmaf(libm.fmaf(-q, 255.0, x), rcp, q))
+        assert got == np.float32(x / np.float32(255.0)), v
+        plain_differs += int(q != np.float32(x / np.float32(255.0)))
+    assert plain_differs > 0                                        # the correction step is needed
+
+
 # ---------------------------------------------------------------- GPU
 def _gl(w, h):
     import rtb200
@@ -74,11 +92,13 @@ def test_cuda_smaa_matches_the_reference_shader(preset, size):
         for seed in (1, 2):
             img = _shapes(w, h, seed)
             want_out, want_edges, want_blend = smaa_ref(img, PRESETS[preset])
-            out, edges, blend, ms = gl.smaa_apply(img)
-            assert np.array_equal(edges, want_edges), f"{preset} {size}: {int((edges != want_edges).any(axis=2).sum())} edge pixels differ"
-            assert np.array_equal(blend, want_blend), f"{preset} {size}: {int((blend != want_blend).any(axis=2).sum())} weight pixels differ"
-            assert np.array_equal(out, want_out), f"{preset} {size}: {int((out != want_out).any(axis=2).sum())} output pixels differ"
-            assert ms > 0
+            for compact in (1, 0):                                  # pass 2 over the compacted edge pixels (default) / over every pixel
+                gl.set_option("smaa_compact", compact)
+                out, edges, blend, ms = gl.smaa_apply(img)
+                assert np.array_equal(edges, want_edges), f"{preset} {size} compact={compact}: {int((edges != want_edges).any(axis=2).sum())} edge pixels differ"
+                assert np.array_equal(blend, want_blend), f"{preset} {size} compact={compact}: {int((blend != want_blend).any(axis=2).sum())} weight pixels differ"
+                assert np.array_equal(out, want_out), f"{preset} {size} compact={compact}: {int((out != want_out).any(axis=2).sum())} output pixels differ"
+                assert ms > 0
     finally:
         gl.stop()
 
