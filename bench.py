@@ -405,6 +405,7 @@ def run_ours(args):
     checksum = float(wl.host_frame[..., :3].double().mean()) if rank == 0 else 0.0
 
     peak = rtb200.measure_fp32_peak(local_rank)
+    peak3 = rtb200.measure_fp32_peak(local_rank, three_registers=True)
     extras = {}
     if not args.no_extras:
         # the other build, same run: value, kernel time, roofline fraction, per-rank kernel times
@@ -509,6 +510,11 @@ def run_ours(args):
                          "traffic": traffic, "ncu": ncu_note, "executed": executed,
                          "kernel": "persistent_kernel" if kstats.kernel_used == 2 else "quad_kernel",
                          "kernel_ms": ms_kernel, "algorithmic_flops_per_launch": local_flops,
+                         "operand_limit": {"three_register_ffma_TFLOPs": peak3, "frac_of_it": achieved / peak3 if peak3 else None,
+                                           "note": "the same FFMA chains as `peak`, but every FFMA reads three distinct registers (acc = p*q + acc) instead of one "
+                                                   "register + a uniform register + a reused operand: the most a sub-partition's register file delivers to FMAs "
+                                                   "that combine three live values, as the Durand-Kerner steps do (tools/micro/rf_probe.cu, "
+                                                   "profiles/r2_rf_probe.txt).  Context only: `frac` is quoted against `peak`."},
                          "peak_source": "FFMA microbenchmark measured in this run (rtb_measure_fp32_peak); MEASURED_PEAKS.json has no fp32 entry; "
                                         "nominal 74.4 = 148 SM x 128 lanes x 2 x 1.965 GHz",
                          "note": "fp32 CUDA-core bound (no dense contraction, north_star).  `achieved` = ALGORITHMIC flops (SURVEY.md 8d constants x exact "

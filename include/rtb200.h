@@ -189,6 +189,9 @@ int rtb_get_stats(rtb_ctx* ctx, rtb_stats* out);
 /* FFMA-only microbenchmark: measured fp32 CUDA-core peak of `device` in
  * TFLOP/s (the roofline denominator; MEASURED_PEAKS.json has none). */
 int rtb_measure_fp32_peak(int device, double* tflops);
+/* The same chains with three distinct register operands per FFMA: what a sub-partition's register file can feed when every
+ * FMA combines three live values (reported beside the peak; never the roofline denominator). */
+int rtb_measure_fp32_peak3(int device, double* tflops);
 
 const char* rtb_last_error(const rtb_ctx* ctx);
 const char* rtb_version(void);

@@ -93,6 +93,7 @@ def load_library() -> C.CDLL:
     L.rtb_device_framebuffer.argtypes = [vp]
     L.rtb_get_stats.argtypes = [vp, C.POINTER(RtbStats)]
     L.rtb_measure_fp32_peak.argtypes = [i, C.POINTER(C.c_double)]
+    L.rtb_measure_fp32_peak3.argtypes = [i, C.POINTER(C.c_double)]
     L.rtb_last_error.restype = C.c_char_p
     L.rtb_last_error.argtypes = [vp]
     L.rtb_version.restype = C.c_char_p
@@ -100,11 +101,13 @@ def load_library() -> C.CDLL:
     return L
 
 
-def measure_fp32_peak(device: int = 0) -> float:
-    """FFMA-only microbenchmark, TFLOP/s."""
+def measure_fp32_peak(device: int = 0, three_registers: bool = False) -> float:
+    """FFMA-only microbenchmark, TFLOP/s.  three_registers: every FFMA reads three distinct registers (the operand-delivery
+    limit) instead of one register + a uniform register + a reused operand (the pipe's peak)."""
     L = load_library()
     out = C.c_double(0)
-    if L.rtb_measure_fp32_peak(device, C.byref(out)) != 0:
+    fn = L.rtb_measure_fp32_peak3 if three_registers else L.rtb_measure_fp32_peak
+    if fn(device, C.byref(out)) != 0:
         raise RtbError("rtb_measure_fp32_peak failed (no CUDA device?)")
     return out.value
 

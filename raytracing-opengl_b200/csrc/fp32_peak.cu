@@ -17,22 +17,44 @@ __global__ void __launch_bounds__(256) ffma_kernel(float* out, int iters, float 
     float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
     if (s == 123.456f) out[0] = s;       /* keeps the chain live without a store in the common case */
 }
+/* The same chains with THREE distinct register operands per FFMA (acc = p_k * q_k + acc; p_k, q_k loop-invariant registers):
+ * the operand-delivery limit of a sub-partition.  The kernel above reads one register per FFMA (a is a uniform register, b sits
+ * in the operand-reuse cache); code whose FMAs combine three live values cannot go faster than this one
+ * (tools/micro/rf_probe.cu, profiles/r2_rf_probe.txt: 1.07 clk per FFMA there, 1.53-1.77 here). */
+__global__ void __launch_bounds__(256) ffma3_kernel(float* out, const float* in, int iters) {
+    float acc[8], p[8], q[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { acc[k] = threadIdx.x * 1e-3f + k; p[k] = in[threadIdx.x + 3 * k]; q[k] = in[64 + threadIdx.x + 5 * k]; }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(acc[k]) : "f"(p[k]), "f"(q[k]));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += acc[k];
+    if (s == 123.456f) out[0] = s;
+}
 }  // namespace
 
-extern "C" int rtb_measure_fp32_peak(int device, double* tflops) {
+static int measure(int device, double* tflops, bool three_registers) {
     if (!tflops) return RTB_ERR_INVALID;
     if (cudaSetDevice(device) != cudaSuccess) return RTB_ERR_NO_DEVICE;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return RTB_ERR_CUDA;
     float* out = nullptr;
-    if (cudaMalloc(&out, 256) != cudaSuccess) return RTB_ERR_CUDA;
+    if (cudaMalloc(&out, 4096) != cudaSuccess) return RTB_ERR_CUDA;
+    cudaMemset(out, 0, 4096);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
     double best = 0.0;
     for (int rep = 0; rep < 6; rep++) {
         cudaEventRecord(e0);
-        ffma_kernel<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+        if (three_registers) ffma3_kernel<<<blocks, threads>>>(out, out + 64, iters);
+        else ffma_kernel<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return RTB_ERR_CUDA; }
         float ms = 0.f;
@@ -46,3 +68,6 @@ extern "C" int rtb_measure_fp32_peak(int device, double* tflops) {
     *tflops = best;
     return RTB_OK;
 }
+
+extern "C" int rtb_measure_fp32_peak(int device, double* tflops) { return measure(device, tflops, false); }
+extern "C" int rtb_measure_fp32_peak3(int device, double* tflops) { return measure(device, tflops, true); }
