@@ -143,7 +143,9 @@ int rtb_set_texture2d(rtb_ctx* ctx, int unit, const uint8_t* pixels, int w, int 
  * the roofline); "ctas_per_sm" (quad kernel); "coop" (0 = switch the persistent kernel's cooperative drain off: an A/B
  * and test switch, results are identical); "gather" (enum rtb_gather_mode, multi-GPU contexts); "smaa_compact" (0 = run
  * SMAA's blending-weight pass over every pixel as the reference draws it instead of over the compacted edge pixels: an
- * A/B and test switch, results are identical). */
+ * A/B and test switch, results are identical); "lpt" (-1 = automatic, the default: on for frames of at least 4096 tiles on the
+ * persistent kernel; 0 / 1 = off / on): from the second frame on, the cheapest tiles of the previous frame are handed out last so
+ * that the frame ends on its shortest paths; the order never changes a pixel. */
 int rtb_set_option(rtb_ctx* ctx, const char* key, int value);
 
 /* GLWrapper::draw()  (GLWrapper.h:34; GLWrapper.cpp:155-165): render one frame

@@ -70,6 +70,10 @@ struct FrameParams {
     float* fb; int32_t fb_global; int32_t rank, world, block_rows, local_rows;
     /* work distribution */
     unsigned int* tile_counter; int32_t n_tiles_x, n_tiles_y;
+    /* persistent kernel, frame loops: tile_cost[t] accumulates the path lengths of tile t's pixels in this frame; tile_perm is
+     * the hand-out order derived from the previous frame's costs (costliest first, so that the frame ends on its cheapest
+     * paths and the drain has little left to do).  Either may be NULL. */
+    unsigned int* tile_cost; const unsigned int* tile_perm;
     /* options */
     int32_t cull;
     int32_t coop;                     /* 1 = cooperative drain (default); 0 = every warp drains alone with serial scans (A/B, tests) */

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
     const int n_lights = P.n_lpoint + P.n_ldirect;
     Counters cnt = {};
 
-    /* path state */
+    /* path state (px: the tile of the lane's pixel, -1 = no path) */
     int px = -1, fb_off = 0;
     vec3 ro = mk3(0, 0, 0), rd = mk3(0, 0, 1), mask = mk3(1, 1, 1), color = mk3(0, 0, 0);
     float absorbDistance = 0.f;
@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
                 unsigned idx = base + __popc(want & ((1u << lane) - 1u));
                 if (idx < total) {
                     int tile = idx >> 5, l = idx & 31;
+                    if (P.tile_perm) tile = (int)__ldg(P.tile_perm + tile);     /* costliest tiles of the previous frame first (rtb_api.cu) */
                     int tx = tile % P.n_tiles_x, ty = tile / P.n_tiles_x;
                     int qd = l >> 2;
                     int x = tx * 8 + (qd & 3) * 2 + (l & 1);
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
                         rd = getRayDir(P, x, y);
                         absorbDistance = 0.f; it = 0; glass = 0;
                         if (COUNT) cnt.pixels++;
-                        if (P.iterations > 0) { px = 1; job = JOB_MAIN; jro = ro; jrd = rd; jlimit = MAX_DIST; }
+                        if (P.iterations > 0) { px = tile; job = JOB_MAIN; jro = ro; jrd = rd; jlimit = MAX_DIST; }
                         else *(float4*)(P.fb + (size_t)fb_off * 4) = make_float4(0.f, 0.f, 0.f, 1.f);
                     }
                 }
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
         }
         if (path_done) {
             *(float4*)(P.fb + (size_t)fb_off * 4) = make_float4(color.x, color.y, color.z, 1.0f);
+            if (P.tile_cost) atomicAdd(P.tile_cost + px, (unsigned)(it + glass + 1));   /* this path's length: the tile's cost for the next frame's order */
             px = -1;
         }
     }

@@ -174,6 +174,57 @@ double algorithmic_flops(const rtb_stats& s) {
     return f;
 }
 
+/* Hand-out order of the next frame's tiles.  The frame should END on its cheapest paths: when the counter runs out every lane
+ * still holds a path, and whatever those paths have left is served by the drain, CTA by CTA, with nobody to share it with —
+ * the CTA with the longest leftovers ends the frame (measured: 3 200 drain jobs against a median of 1 900).  So the cheapest
+ * tiles of the previous frame (cost = summed path lengths of the tile's 32 pixels; as many as `tail`, taken bucket by bucket
+ * from the cheap end) go LAST, costliest bucket first, and all other tiles keep the scan order.  Measured (tools/lpt_ab.py,
+ * profiles/r2_lpt_ab.jsonl): whole 4K frames 0.3-1.7 % faster, one share of an 8-way split 2.4-3.2 % (the drain is 10 % of
+ * such a frame).  Sorting the WHOLE frame by cost gains 3.9 % on a share but loses 1-2.4 % on whole frames: neighbouring
+ * lanes then hold unrelated pixels.  One CTA, 1024 tiles per step. */
+__device__ __forceinline__ unsigned cost_bucket(unsigned c) { c >>= 2; return c > 255u ? 255u : c; }
+__global__ void __launch_bounds__(1024) tile_order_kernel(const unsigned* __restrict__ cost, unsigned* __restrict__ perm, int n, int tail) {
+    __shared__ unsigned hist[256], cursor[256], warp_cnt[32];
+    __shared__ unsigned split, quota, taken, cur_head;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    if (t < 256) hist[t] = 0;
+    __syncthreads();
+    for (int i = t; i < n; i += 1024) atomicAdd(&hist[cost_bucket(cost[i])], 1u);
+    __syncthreads();
+    if (t == 0) {
+        const unsigned want = min((unsigned)tail, (unsigned)n / 2u);
+        unsigned cum = 0, b = 0;
+        while (b < 255u && cum + hist[b] <= want) cum += hist[b++];              /* buckets 0..b-1 go last entirely ... */
+        const unsigned q = min(hist[b], want - cum);                             /* ... and q tiles of bucket b (a frame that is half sky has one huge cheapest bucket) */
+        split = b; quota = q; taken = 0; cur_head = 0;
+        unsigned o = (unsigned)n - (cum + q);                                    /* the tail: bucket b first, bucket 0 last */
+        cursor[b] = o; o += q;
+        for (int k = (int)b - 1; k >= 0; k--) { cursor[k] = o; o += hist[k]; }
+    }
+    __syncthreads();
+    const unsigned sp = split;
+    unsigned bucket = t < n ? cost_bucket(cost[t]) : 0u;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + t;
+        const bool valid = i < n;
+        const unsigned my_bucket = bucket;
+        bool is_tail = valid && my_bucket < sp;
+        if (valid && my_bucket == sp) is_tail = atomicAdd(&taken, 1u) < quota;
+        if (i + 1024 < n) bucket = cost_bucket(cost[i + 1024]);                  /* the next step's cost arrives behind this step's barriers */
+        const bool is_head = valid && !is_tail;
+        const unsigned m = __ballot_sync(0xffffffffu, is_head);
+        if (lane == 0) warp_cnt[wid] = (unsigned)__popc(m);
+        __syncthreads();
+        unsigned before = 0, all = 0;
+        for (int w = 0; w < 32; w++) { const unsigned c = warp_cnt[w]; if (w < wid) before += c; all += c; }
+        if (is_head) perm[cur_head + before + (unsigned)__popc(m & ((1u << lane) - 1u))] = (unsigned)i;      /* stable: the scan order */
+        if (is_tail) perm[atomicAdd(&cursor[my_bucket], 1u)] = (unsigned)i;                                  /* by bucket; scan order to within this step */
+        __syncthreads();
+        if (t == 0) cur_head += all;
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 int rtb_do_render(rtb_ctx* ctx, float* target, bool target_global_rows, cudaStream_t st, bool counted, bool timed) {
@@ -220,6 +271,7 @@ int rtb_do_render(rtb_ctx* ctx, float* target, bool target_global_rows, cudaStre
     P.fb = target; P.fb_global = target_global_rows ? 1 : 0; P.rank = ctx->rank; P.world = ctx->world; P.block_rows = ctx->block_rows; P.local_rows = ctx->local_rows;
     P.tile_counter = ctx->tile_counter;
     P.n_tiles_x = (ctx->width + 7) / 8; P.n_tiles_y = (ctx->local_rows + 3) / 4;
+    P.tile_cost = nullptr; P.tile_perm = nullptr;
     P.cull = ctx->opt_cull;
     P.coop = ctx->opt_coop;
     P.k_one = 1.0f; P.k_neg_zero = -0.0f; P.k_neg_one = -1.0f;
@@ -261,6 +313,21 @@ int rtb_do_render(rtb_ctx* ctx, float* target, bool target_global_rows, cudaStre
         if (pe) return fail(ctx, RTB_ERR_CUDA, "pack kernel launch: %s", cudaGetErrorString((cudaError_t)pe));
         ctx->dirty = false;
     }
+    /* cost-ordered tiles (option "lpt": -1 = automatic, frames of at least 4096 tiles on the persistent kernel) */
+    const int n_tiles = P.n_tiles_x * P.n_tiles_y;
+    const bool lpt = kernel == RTB_KERNEL_PERSISTENT && (ctx->opt_lpt > 0 || (ctx->opt_lpt < 0 && n_tiles >= 4096));
+    if (lpt) {
+        if (ctx->lpt_tiles != n_tiles) {                   /* first frame, or the partition changed: no order yet */
+            if (ctx->tile_cost) { CU(cudaFreeAsync(ctx->tile_cost, ctx->stream)); CU(cudaFreeAsync(ctx->tile_perm, ctx->stream)); }
+            CU(cudaMallocAsync((void**)&ctx->tile_cost, (size_t)n_tiles * sizeof(unsigned), ctx->stream));
+            CU(cudaMallocAsync((void**)&ctx->tile_perm, (size_t)n_tiles * sizeof(unsigned), ctx->stream));
+            ctx->lpt_tiles = n_tiles; ctx->lpt_valid = false;
+            if (st != ctx->stream) { CU(cudaEventRecord(ctx->ev_order, ctx->stream)); CU(cudaStreamWaitEvent(st, ctx->ev_order, 0)); }
+        }
+        CU(cudaMemsetAsync(ctx->tile_cost, 0, (size_t)n_tiles * sizeof(unsigned), st));
+        P.tile_cost = ctx->tile_cost;
+        P.tile_perm = ctx->lpt_valid ? ctx->tile_perm : nullptr;
+    }
     CU(cudaMemsetAsync(ctx->tile_counter, 0, sizeof(unsigned int), st));
     if (counted) CU(cudaMemsetAsync(ctx->counters, 0, CNT_NUM * sizeof(unsigned long long), st));
     if (timed) CU(cudaEventRecord(ctx->ev0, st));
@@ -268,6 +335,14 @@ int rtb_do_render(rtb_ctx* ctx, float* target, bool target_global_rows, cudaStre
                : rtb_fast_launch(&P, launch_kernel, counted ? 1 : 0, grid, threads, smem, st);
     if (e) return fail(ctx, RTB_ERR_CUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)e));
     if (timed) { CU(cudaEventRecord(ctx->ev1, st)); ctx->timed_pending = true; }
+    if (lpt) {
+        /* the tail: three times the tiles whose pixels are in flight when the counter runs out */
+        int tail_factor = 3;
+        if (const char* e = getenv("RTB_LPT_TAIL")) tail_factor = atoi(e) > 0 ? atoi(e) : 3;      /* development */
+        tile_order_kernel<<<1, 1024, 0, st>>>(ctx->tile_cost, ctx->tile_perm, n_tiles, tail_factor * (grid * threads / 32));
+        CU(cudaGetLastError());
+        ctx->lpt_valid = true;
+    }
     if (st != ctx->stream) {
         /* ... and order the context stream behind this frame: the next upload overwrites the arrays the kernels are reading,
          * the next frame reuses the packed block and the tile counter */
@@ -326,6 +401,7 @@ void rtb_destroy(rtb_ctx* ctx) {
     for (int b = 0; b < RTB_NUM_BINDINGS; b++) if (ctx->raw[b]) cudaFree(ctx->raw[b]);
     if (ctx->packed) cudaFree(ctx->packed);
     if (ctx->tile_counter) cudaFree(ctx->tile_counter);
+    if (ctx->tile_cost) { cudaFree(ctx->tile_cost); cudaFree(ctx->tile_perm); }
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->cta_times) cudaFree(ctx->cta_times);
     if (ctx->fb) cudaFree(ctx->fb);
@@ -345,6 +421,7 @@ int rtb_set_partition(rtb_ctx* ctx, int rank, int world, int block_rows) {
         return fail(ctx, RTB_ERR_INVALID, "bad partition rank %d / world %d / block_rows %d (block_rows must be a multiple of 4)", rank, world, block_rows);
     ctx->rank = rank; ctx->world = world; ctx->block_rows = block_rows;
     ctx->local_rows = rtb_compute_local_rows(ctx->height, rank, world, block_rows);
+    ctx->lpt_valid = false;                               /* the tile order belongs to the previous share of the frame */
     return RTB_OK;
 }
 
@@ -452,6 +529,7 @@ int rtb_set_option(rtb_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "ctas_per_sm")) ctx->opt_ctas_per_sm = value;
     else if (!strcmp(key, "coop")) ctx->opt_coop = value ? 1 : 0;
     else if (!strcmp(key, "smaa_compact")) ctx->opt_smaa_compact = value ? 1 : 0;
+    else if (!strcmp(key, "lpt")) { ctx->opt_lpt = value < 0 ? -1 : (value ? 1 : 0); ctx->lpt_valid = false; }
     else if (!strcmp(key, "gather")) { if (value != RTB_GATHER_NCCL && value != RTB_GATHER_P2P) return fail(ctx, RTB_ERR_INVALID, "gather must be 0 (NCCL) or 1 (P2P)");
         if (value == RTB_GATHER_P2P && (ctx->peers.empty() || !ctx->p2p_ok)) return fail(ctx, RTB_ERR_STATE, "P2P gather needs a multi-device context whose GPUs have peer access to device 0");
         ctx->opt_gather = value; }

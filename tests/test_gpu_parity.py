@@ -422,3 +422,41 @@ def test_cooperative_drain_is_bit_identical_to_the_serial_drain(seed, procedural
     a, _ = gpu_render(sc, procedural, kernel=KERNEL_PERSISTENT, coop=1)
     b, _ = gpu_render(sc, procedural, kernel=KERNEL_PERSISTENT, coop=0)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("strict", (1, 0))
+def test_cost_ordered_tiles_render_the_same_frames(strict, procedural):
+    """Option "lpt": from the second frame on the persistent kernel hands its tiles out costliest first (the order is a
+    counting sort of the previous frame's per-tile path lengths, rtb_api.cu tile_order_kernel).  Pixels are independent, so
+    every frame — the first in scan order, the later ones in cost order, also after the camera moved and the order is stale —
+    carries the bits of a frame rendered with the option off, and the work counters stay equal."""
+    sc = scenes.build_config("mixed1024_4k", 1 / 6)                # 640x360: 3600 tiles -> switch the option on explicitly
+    w, h = int(sc.scene["canvas_width"]), int(sc.scene["canvas_height"])
+    frames = {}
+    for lpt in (0, 1):
+        gl = rtb200.GLWrapper(w, h)
+        gl.init_window()
+        try:
+            handles = rtb200.setup_scene(gl, sc, procedural)
+            gl.set_option("kernel", KERNEL_PERSISTENT)
+            gl.set_option("strict", strict)
+            gl.set_option("lpt", lpt)
+            out = []
+            for k in range(3):
+                gl.draw()
+                out.append(gl.read_pixels())
+            scene2 = sc.scene.copy()
+            scene2["camera_pos"][0] += 0.75                        # frame 4: the camera moved, the order is the old frame's
+            gl.update_buffer(handles["scene_buf"], np.ascontiguousarray(scene2).reshape(1))
+            gl.draw()
+            out.append(gl.read_pixels())
+            out.append(gl.draw_counted().as_dict())
+            frames[lpt] = out
+        finally:
+            gl.stop()
+    for k in range(4):
+        assert np.array_equal(frames[0][k].view(np.uint32), frames[1][k].view(np.uint32)), k
+    assert np.array_equal(frames[1][0].view(np.uint32), frames[1][2].view(np.uint32))
+    assert not np.array_equal(frames[1][2], frames[1][3])         # the camera did move
+    work = [{k: v for k, v in frames[lpt][4].items() if not k.endswith("_ms")} for lpt in (0, 1)]
+    assert work[0] == work[1] and work[0]["dk_iterations"] > 0
