@@ -181,48 +181,97 @@ double algorithmic_flops(const rtb_stats& s) {
  * from the cheap end) go LAST, costliest bucket first, and all other tiles keep the scan order.  Measured (tools/lpt_ab.py,
  * profiles/r2_lpt_ab.jsonl): whole 4K frames 0.3-1.7 % faster, one share of an 8-way split 2.4-3.2 % (the drain is 10 % of
  * such a frame).  Sorting the WHOLE frame by cost gains 3.9 % on a share but loses 1-2.4 % on whole frames: neighbouring
- * lanes then hold unrelated pixels.  One CTA, 1024 tiles per step. */
+ * lanes then hold unrelated pixels.  Three small kernels (histogram per 4096-tile chunk, plan, scatter). */
 __device__ __forceinline__ unsigned cost_bucket(unsigned c) { c >>= 2; return c > 255u ? 255u : c; }
-__global__ void __launch_bounds__(1024) tile_order_kernel(const unsigned* __restrict__ cost, unsigned* __restrict__ perm, int n, int tail) {
-    __shared__ unsigned hist[256], cursor[256], warp_cnt[32];
-    __shared__ unsigned split, quota, taken, cur_head;
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+constexpr int ORDER_CHUNK = 4096;                                  /* tiles per CTA: four consecutive ones per thread */
+struct OrderPlan { unsigned split, quota, tail_start[256]; };      /* written by tile_plan_kernel, read by tile_scatter_kernel */
+
+/* one warp-wide add per distinct value instead of one shared-memory atomic per lane (half the tiles of a frame can share one
+ * bucket — sky); returns this lane's rank among the lanes with its key.  Every lane of the warp must call it. */
+__device__ __forceinline__ unsigned warp_add_by_key(unsigned* counters, unsigned key, bool valid, unsigned lane) {
+    const unsigned same = __match_any_sync(0xffffffffu, valid ? key : 0xffffffffu);
+    unsigned base = 0;
+    const int leader = __ffs(same) - 1;
+    if (valid && (int)lane == leader) base = atomicAdd(&counters[key], (unsigned)__popc(same));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (unsigned)__popc(same & ((1u << lane) - 1u));
+}
+/* 1: the cost histogram of every chunk */
+__global__ void __launch_bounds__(1024) tile_hist_kernel(const unsigned* __restrict__ cost, unsigned* __restrict__ chunk_hist, int n) {
+    __shared__ unsigned hist[256];
+    const int t = threadIdx.x, i0 = blockIdx.x * ORDER_CHUNK + 4 * t;
     if (t < 256) hist[t] = 0;
     __syncthreads();
-    for (int i = t; i < n; i += 1024) atomicAdd(&hist[cost_bucket(cost[i])], 1u);
+    const uint4 c = *(const uint4*)(cost + i0);                     /* the array is allocated and zeroed up to a whole chunk */
+    const unsigned cs[4] = { c.x, c.y, c.z, c.w };
+#pragma unroll
+    for (int j = 0; j < 4; j++) warp_add_by_key(hist, cost_bucket(cs[j]), i0 + j < n, t & 31);
     __syncthreads();
-    if (t == 0) {
+    if (t < 256) chunk_hist[blockIdx.x * 256 + t] = hist[t];
+}
+/* 2: which buckets form the tail, and for every chunk and bucket the number of such tiles in the chunks before it (in place) */
+__global__ void __launch_bounds__(256) tile_plan_kernel(unsigned* __restrict__ chunk_hist, OrderPlan* __restrict__ plan, int n, int n_chunks, int tail) {
+    __shared__ unsigned total[256];
+    const int k = threadIdx.x;
+    unsigned sum = 0;
+    for (int c = 0; c < n_chunks; c++) { const unsigned v = chunk_hist[c * 256 + k]; chunk_hist[c * 256 + k] = sum; sum += v; }
+    total[k] = sum;
+    __syncthreads();
+    if (k == 0) {
         const unsigned want = min((unsigned)tail, (unsigned)n / 2u);
         unsigned cum = 0, b = 0;
-        while (b < 255u && cum + hist[b] <= want) cum += hist[b++];              /* buckets 0..b-1 go last entirely ... */
-        const unsigned q = min(hist[b], want - cum);                             /* ... and q tiles of bucket b (a frame that is half sky has one huge cheapest bucket) */
-        split = b; quota = q; taken = 0; cur_head = 0;
+        while (b < 255u && cum + total[b] <= want) cum += total[b++];            /* buckets 0..b-1 go last entirely ... */
+        const unsigned q = min(total[b], want - cum);                            /* ... and the first q tiles of bucket b (a frame that is half sky has one huge cheapest bucket) */
+        plan->split = b; plan->quota = q;
         unsigned o = (unsigned)n - (cum + q);                                    /* the tail: bucket b first, bucket 0 last */
-        cursor[b] = o; o += q;
-        for (int k = (int)b - 1; k >= 0; k--) { cursor[k] = o; o += hist[k]; }
+        plan->tail_start[b] = o; o += q;
+        for (int j = (int)b - 1; j >= 0; j--) { plan->tail_start[j] = o; o += total[j]; }
+    }
+}
+/* 3: every chunk places its tiles: heads in scan order (a stable partition), tails by bucket */
+__global__ void __launch_bounds__(1024) tile_scatter_kernel(const unsigned* __restrict__ cost, const unsigned* __restrict__ chunk_prefix,
+                                                            const OrderPlan* __restrict__ plan, unsigned* __restrict__ perm, int n) {
+    __shared__ unsigned cursor[256], warp_cnt[32], red[8];
+    __shared__ unsigned taken;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5, i0 = blockIdx.x * ORDER_CHUNK + 4 * t;
+    const unsigned sp = plan->split, quota = plan->quota;
+    unsigned before_tail = 0;                                       /* tail tiles in the chunks before this one */
+    if (t < 256) {
+        const unsigned pre = chunk_prefix[blockIdx.x * 256 + t];
+        cursor[t] = (t <= (int)sp ? plan->tail_start[t] : 0u) + ((unsigned)t == sp ? min(pre, quota) : pre);
+        before_tail = (unsigned)t < sp ? pre : ((unsigned)t == sp ? min(pre, quota) : 0u);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) before_tail += __shfl_xor_sync(0xffffffffu, before_tail, d);
+        if (lane == 0) red[wid] = before_tail;
+        if ((unsigned)t == sp) taken = min(pre, quota);
     }
     __syncthreads();
-    const unsigned sp = split;
-    unsigned bucket = t < n ? cost_bucket(cost[t]) : 0u;
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + t;
-        const bool valid = i < n;
-        const unsigned my_bucket = bucket;
-        bool is_tail = valid && my_bucket < sp;
-        if (valid && my_bucket == sp) is_tail = atomicAdd(&taken, 1u) < quota;
-        if (i + 1024 < n) bucket = cost_bucket(cost[i + 1024]);                  /* the next step's cost arrives behind this step's barriers */
-        const bool is_head = valid && !is_tail;
-        const unsigned m = __ballot_sync(0xffffffffu, is_head);
-        if (lane == 0) warp_cnt[wid] = (unsigned)__popc(m);
-        __syncthreads();
-        unsigned before = 0, all = 0;
-        for (int w = 0; w < 32; w++) { const unsigned c = warp_cnt[w]; if (w < wid) before += c; all += c; }
-        if (is_head) perm[cur_head + before + (unsigned)__popc(m & ((1u << lane) - 1u))] = (unsigned)i;      /* stable: the scan order */
-        if (is_tail) perm[atomicAdd(&cursor[my_bucket], 1u)] = (unsigned)i;                                  /* by bucket; scan order to within this step */
-        __syncthreads();
-        if (t == 0) cur_head += all;
-        __syncthreads();
+    before_tail = red[0] + red[1] + red[2] + red[3] + red[4] + red[5] + red[6] + red[7];
+    const uint4 c = *(const uint4*)(cost + i0);
+    const unsigned cs[4] = { c.x, c.y, c.z, c.w };
+    bool is_head[4];
+    unsigned mine = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const bool valid = i0 + j < n;
+        const unsigned bk = cost_bucket(cs[j]);
+        bool is_tail = valid && bk < sp;
+        if (valid && bk == sp && *(volatile unsigned*)&taken < quota) is_tail = atomicAdd(&taken, 1u) < quota;   /* the quota runs out in ONE chunk */
+        is_head[j] = valid && !is_tail;
+        mine += is_head[j] ? 1u : 0u;
+        const unsigned pos = warp_add_by_key(cursor, bk, is_tail, lane);
+        if (is_tail) perm[pos] = (unsigned)(i0 + j);
     }
+    unsigned incl = mine;                                           /* inclusive scan of the head counts over the warp */
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    if (lane == 31) warp_cnt[wid] = incl;
+    __syncthreads();
+    unsigned before = 0;
+    for (int w = 0; w < wid; w++) before += warp_cnt[w];
+    unsigned pos = (unsigned)(blockIdx.x * ORDER_CHUNK) - before_tail + before + incl - mine;
+#pragma unroll
+    for (int j = 0; j < 4; j++) if (is_head[j]) perm[pos++] = (unsigned)(i0 + j);      /* stable: the scan order */
 }
 
 }  // namespace
@@ -318,13 +367,15 @@ int rtb_do_render(rtb_ctx* ctx, float* target, bool target_global_rows, cudaStre
     const bool lpt = kernel == RTB_KERNEL_PERSISTENT && (ctx->opt_lpt > 0 || (ctx->opt_lpt < 0 && n_tiles >= 4096));
     if (lpt) {
         if (ctx->lpt_tiles != n_tiles) {                   /* first frame, or the partition changed: no order yet */
-            if (ctx->tile_cost) { CU(cudaFreeAsync(ctx->tile_cost, ctx->stream)); CU(cudaFreeAsync(ctx->tile_perm, ctx->stream)); }
-            CU(cudaMallocAsync((void**)&ctx->tile_cost, (size_t)n_tiles * sizeof(unsigned), ctx->stream));
-            CU(cudaMallocAsync((void**)&ctx->tile_perm, (size_t)n_tiles * sizeof(unsigned), ctx->stream));
+            if (ctx->tile_cost) { CU(cudaFreeAsync(ctx->tile_cost, ctx->stream)); CU(cudaFreeAsync(ctx->tile_perm, ctx->stream)); CU(cudaFreeAsync(ctx->tile_hist, ctx->stream)); }
+            const size_t chunks = ((size_t)n_tiles + ORDER_CHUNK - 1) / ORDER_CHUNK;                  /* costs are read a whole chunk at a time */
+            CU(cudaMallocAsync((void**)&ctx->tile_cost, chunks * ORDER_CHUNK * sizeof(unsigned), ctx->stream));
+            CU(cudaMallocAsync((void**)&ctx->tile_perm, chunks * ORDER_CHUNK * sizeof(unsigned), ctx->stream));
+            CU(cudaMallocAsync((void**)&ctx->tile_hist, chunks * 256 * sizeof(unsigned) + sizeof(OrderPlan), ctx->stream));
             ctx->lpt_tiles = n_tiles; ctx->lpt_valid = false;
             if (st != ctx->stream) { CU(cudaEventRecord(ctx->ev_order, ctx->stream)); CU(cudaStreamWaitEvent(st, ctx->ev_order, 0)); }
         }
-        CU(cudaMemsetAsync(ctx->tile_cost, 0, (size_t)n_tiles * sizeof(unsigned), st));
+        CU(cudaMemsetAsync(ctx->tile_cost, 0, (size_t)((n_tiles + ORDER_CHUNK - 1) / ORDER_CHUNK) * ORDER_CHUNK * sizeof(unsigned), st));
         P.tile_cost = ctx->tile_cost;
         P.tile_perm = ctx->lpt_valid ? ctx->tile_perm : nullptr;
     }
@@ -339,7 +390,11 @@ int rtb_do_render(rtb_ctx* ctx, float* target, bool target_global_rows, cudaStre
         /* the tail: three times the tiles whose pixels are in flight when the counter runs out */
         int tail_factor = 3;
         if (const char* e = getenv("RTB_LPT_TAIL")) tail_factor = atoi(e) > 0 ? atoi(e) : 3;      /* development */
-        tile_order_kernel<<<1, 1024, 0, st>>>(ctx->tile_cost, ctx->tile_perm, n_tiles, tail_factor * (grid * threads / 32));
+        const int chunks = (n_tiles + ORDER_CHUNK - 1) / ORDER_CHUNK;
+        OrderPlan* plan = (OrderPlan*)(ctx->tile_hist + (size_t)chunks * 256);
+        tile_hist_kernel<<<chunks, 1024, 0, st>>>(ctx->tile_cost, ctx->tile_hist, n_tiles);
+        tile_plan_kernel<<<1, 256, 0, st>>>(ctx->tile_hist, plan, n_tiles, chunks, tail_factor * (grid * threads / 32));
+        tile_scatter_kernel<<<chunks, 1024, 0, st>>>(ctx->tile_cost, ctx->tile_hist, plan, ctx->tile_perm, n_tiles);
         CU(cudaGetLastError());
         ctx->lpt_valid = true;
     }
@@ -401,7 +456,7 @@ void rtb_destroy(rtb_ctx* ctx) {
     for (int b = 0; b < RTB_NUM_BINDINGS; b++) if (ctx->raw[b]) cudaFree(ctx->raw[b]);
     if (ctx->packed) cudaFree(ctx->packed);
     if (ctx->tile_counter) cudaFree(ctx->tile_counter);
-    if (ctx->tile_cost) { cudaFree(ctx->tile_cost); cudaFree(ctx->tile_perm); }
+    if (ctx->tile_cost) { cudaFree(ctx->tile_cost); cudaFree(ctx->tile_perm); cudaFree(ctx->tile_hist); }
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->cta_times) cudaFree(ctx->cta_times);
     if (ctx->fb) cudaFree(ctx->fb);

@@ -37,7 +37,7 @@ struct rtb_ctx {
     uint8_t* packed = nullptr; size_t packed_cap = 0;
     bool dirty = true;
     unsigned int* tile_counter = nullptr;
-    unsigned int *tile_cost = nullptr, *tile_perm = nullptr;   /* persistent kernel: per-tile path lengths of the last frame and the order derived from them */
+    unsigned int *tile_cost = nullptr, *tile_perm = nullptr, *tile_hist = nullptr;   /* persistent kernel: per-tile path lengths of the last frame and the order derived from them */
     int lpt_tiles = 0, opt_lpt = -1;
     bool lpt_valid = false;
     unsigned long long* counters = nullptr;

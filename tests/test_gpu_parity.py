@@ -427,7 +427,7 @@ def test_cooperative_drain_is_bit_identical_to_the_serial_drain(seed, procedural
 @pytest.mark.parametrize("strict", (1, 0))
 def test_cost_ordered_tiles_render_the_same_frames(strict, procedural):
     """Option "lpt": from the second frame on the persistent kernel hands its tiles out costliest first (the order is a
-    counting sort of the previous frame's per-tile path lengths, rtb_api.cu tile_order_kernel).  Pixels are independent, so
+    counting sort of the previous frame's per-tile path lengths, rtb_api.cu tile_hist / tile_plan / tile_scatter_kernel).  Pixels are independent, so
     every frame — the first in scan order, the later ones in cost order, also after the camera moved and the order is stale —
     carries the bits of a frame rendered with the option off, and the work counters stay equal."""
     sc = scenes.build_config("mixed1024_4k", 1 / 6)                # 640x360: 3600 tiles -> switch the option on explicitly
