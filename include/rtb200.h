@@ -145,7 +145,8 @@ int rtb_set_texture2d(rtb_ctx* ctx, int unit, const uint8_t* pixels, int w, int 
  * SMAA's blending-weight pass over every pixel as the reference draws it instead of over the compacted edge pixels: an
  * A/B and test switch, results are identical); "lpt" (-1 = automatic, the default: on for frames of at least 4096 tiles on the
  * persistent kernel; 0 / 1 = off / on): from the second frame on, the cheapest tiles of the previous frame are handed out last so
- * that the frame ends on its shortest paths; the order never changes a pixel. */
+ * that the frame ends on its shortest paths; the order never changes a pixel; "wide" (-1 = automatic, the default: scenes without
+ * tori run the fused build's persistent kernel with 24 warps of 80 registers instead of 20 warps of 96; 0 / 1 = off / on; same bits). */
 int rtb_set_option(rtb_ctx* ctx, const char* key, int value);
 
 /* GLWrapper::draw()  (GLWrapper.h:34; GLWrapper.cpp:155-165): render one frame

@@ -351,8 +351,13 @@ extern "C" int CAT(RTB_NS, _launch)(const FrameParams* P, int kernel, int counte
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         k<<<grid, QUAD_THREADS, smem, st>>>(*P);
+    } else if (kernel == RTB_LAUNCH_PERSISTENT_WIDE) {
+        auto k = counted ? RTB_NS::persistent_kernel<true, PERSIST_THREADS_WIDE> : RTB_NS::persistent_kernel<false, PERSIST_THREADS_WIDE>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        k<<<grid, PERSIST_THREADS_WIDE, smem, st>>>(*P);
     } else {
-        auto k = counted ? RTB_NS::persistent_kernel<true> : RTB_NS::persistent_kernel<false>;
+        auto k = counted ? RTB_NS::persistent_kernel<true, PERSIST_THREADS> : RTB_NS::persistent_kernel<false, PERSIST_THREADS>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         k<<<grid, PERSIST_THREADS, smem, st>>>(*P);
@@ -367,10 +372,14 @@ extern "C" int CAT(RTB_NS, _occupancy)(int kernel, size_t smem, int* blocks_per_
         e = cudaFuncSetAttribute(RTB_NS::quad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, RTB_NS::quad_kernel<false>, QUAD_THREADS, smem);
-    } else {
-        e = cudaFuncSetAttribute(RTB_NS::persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    } else if (kernel == RTB_LAUNCH_PERSISTENT_WIDE) {
+        e = cudaFuncSetAttribute(RTB_NS::persistent_kernel<false, PERSIST_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, RTB_NS::persistent_kernel<false>, PERSIST_THREADS, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, RTB_NS::persistent_kernel<false, PERSIST_THREADS_WIDE>, PERSIST_THREADS_WIDE, smem);
+    } else {
+        e = cudaFuncSetAttribute(RTB_NS::persistent_kernel<false, PERSIST_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, RTB_NS::persistent_kernel<false, PERSIST_THREADS>, PERSIST_THREADS, smem);
     }
     return (int)e;
 }

@@ -12,13 +12,17 @@
 #ifndef PERSIST_THREADS
 #define PERSIST_THREADS 640
 #endif
+/* scenes without tori: 24 warps / 80 registers (fused build: spheres4k 17.9 -> 16.7 ms, profiles/r2_fused_thread_variants_ab.jsonl) */
+#define PERSIST_THREADS_WIDE 768
 #ifndef PERSIST_MIN_BLOCKS
 #define PERSIST_MIN_BLOCKS 1
 #endif
 /* dynamic shared memory of the persistent kernel: staged scene (rounded up to 128 B) + one 32-B job and one 32-B result per thread */
-#define PERSIST_SMEM_BYTES(scene_bytes) ((((size_t)(scene_bytes) + 127u) & ~(size_t)127u) + (size_t)PERSIST_THREADS * 64u)
+#define PERSIST_SMEM_BYTES_T(scene_bytes, threads) ((((size_t)(scene_bytes) + 127u) & ~(size_t)127u) + (size_t)(threads) * 64u)
+#define PERSIST_SMEM_BYTES(scene_bytes) PERSIST_SMEM_BYTES_T(scene_bytes, PERSIST_THREADS)
 #define RTB_LAUNCH_QUAD 1
 #define RTB_LAUNCH_PERSISTENT 2
+#define RTB_LAUNCH_PERSISTENT_WIDE 3
 
 #ifdef __cplusplus
 extern "C" {

@@ -43,8 +43,10 @@ enum { COMB_REFRACT_SUB = 0, COMB_REFLECT = 1, COMB_DIFFUSE = 2 };
 struct DrainJob { float ro[3], rd[3], limit; int shadow; };             /* 32 B */
 struct DrainResult { float tm; int id; float shadow, u, v; int _pad[3]; };   /* 32 B */
 
-template <bool COUNT>
-__global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persistent_kernel(const __grid_constant__ FrameParams P) {
+/* THREADS: 640 (20 warps, 96 registers: what the Durand-Kerner solve needs without spilling into its loop) or PERSIST_THREADS_WIDE
+ * (24 warps, 80 registers) for scenes without tori, which are bound by the sphere / box / quadric tests and gain from the extra warps. */
+template <bool COUNT, int THREADS>
+__global__ void __launch_bounds__(THREADS, PERSIST_MIN_BLOCKS) persistent_kernel(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ int drain_flag;                                  /* 0 -> 1 once; read and written with atomics only */
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, PERSIST_MIN_BLOCKS) persisten
     stage_scene_tma(smem, &mbar, P.packed, P.lay.total_bytes);          /* contains the __syncthreads that publishes the zeros above */
     const SceneView S = make_view(smem, P.lay);
     DrainJob* const jobs = (DrainJob*)(smem + ((P.lay.total_bytes + 127u) & ~127u));
-    DrainResult* const results = (DrainResult*)(jobs + PERSIST_THREADS);
+    DrainResult* const results = (DrainResult*)(jobs + THREADS);
 
     const int lane = threadIdx.x & 31;
     const unsigned total = (unsigned)(P.n_tiles_x * P.n_tiles_y) * 32u;

@@ -332,9 +332,12 @@ int rtb_do_render(rtb_ctx* ctx, float* target, bool target_global_rows, cudaStre
     if (kernel == RTB_KERNEL_AUTO) kernel = textured ? RTB_KERNEL_QUAD : RTB_KERNEL_PERSISTENT;
     if (kernel == RTB_KERNEL_PERSISTENT && textured)
         return fail(ctx, RTB_ERR_STATE, "the persistent kernel cannot render scenes that reference 2-D textures (textureNum != 0)");
-    const int launch_kernel = kernel == RTB_KERNEL_QUAD ? RTB_LAUNCH_QUAD : RTB_LAUNCH_PERSISTENT;
-    const int threads = kernel == RTB_KERNEL_QUAD ? QUAD_THREADS : PERSIST_THREADS;
-    const size_t smem = kernel == RTB_KERNEL_QUAD ? (size_t)P.lay.total_bytes : PERSIST_SMEM_BYTES(P.lay.total_bytes);
+    /* scenes without tori need no room for the Durand-Kerner state: the 24-warp variant (option "wide": -1 = automatic: fused build
+     * only — spheres4k 17.85 -> 16.75 ms; the strict build spills at 80 registers and loses 4 %, profiles/r2_wide_ab.jsonl) */
+    const bool wide = kernel == RTB_KERNEL_PERSISTENT && (ctx->opt_wide > 0 || (ctx->opt_wide < 0 && d.torus_size == 0 && !strict));
+    const int launch_kernel = kernel == RTB_KERNEL_QUAD ? RTB_LAUNCH_QUAD : (wide ? RTB_LAUNCH_PERSISTENT_WIDE : RTB_LAUNCH_PERSISTENT);
+    const int threads = kernel == RTB_KERNEL_QUAD ? QUAD_THREADS : (wide ? PERSIST_THREADS_WIDE : PERSIST_THREADS);
+    const size_t smem = kernel == RTB_KERNEL_QUAD ? (size_t)P.lay.total_bytes : PERSIST_SMEM_BYTES_T(P.lay.total_bytes, threads);
     if (smem > 227 * 1024) return fail(ctx, RTB_ERR_INVALID, "packed scene (%zu bytes) exceeds the 227 KB shared-memory budget", smem);
 
     int per_sm = 0;
@@ -584,6 +587,7 @@ int rtb_set_option(rtb_ctx* ctx, const char* key, int value) {
     else if (!strcmp(key, "ctas_per_sm")) ctx->opt_ctas_per_sm = value;
     else if (!strcmp(key, "coop")) ctx->opt_coop = value ? 1 : 0;
     else if (!strcmp(key, "smaa_compact")) ctx->opt_smaa_compact = value ? 1 : 0;
+    else if (!strcmp(key, "wide")) ctx->opt_wide = value < 0 ? -1 : (value ? 1 : 0);
     else if (!strcmp(key, "lpt")) { ctx->opt_lpt = value < 0 ? -1 : (value ? 1 : 0); ctx->lpt_valid = false; }
     else if (!strcmp(key, "gather")) { if (value != RTB_GATHER_NCCL && value != RTB_GATHER_P2P) return fail(ctx, RTB_ERR_INVALID, "gather must be 0 (NCCL) or 1 (P2P)");
         if (value == RTB_GATHER_P2P && (ctx->peers.empty() || !ctx->p2p_ok)) return fail(ctx, RTB_ERR_STATE, "P2P gather needs a multi-device context whose GPUs have peer access to device 0");

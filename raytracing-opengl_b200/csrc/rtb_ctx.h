@@ -38,7 +38,7 @@ struct rtb_ctx {
     bool dirty = true;
     unsigned int* tile_counter = nullptr;
     unsigned int *tile_cost = nullptr, *tile_perm = nullptr, *tile_hist = nullptr;   /* persistent kernel: per-tile path lengths of the last frame and the order derived from them */
-    int lpt_tiles = 0, opt_lpt = -1;
+    int lpt_tiles = 0, opt_lpt = -1, opt_wide = -1;
     bool lpt_valid = false;
     unsigned long long* counters = nullptr;
     unsigned long long* cta_times = nullptr;     /* RTB_DEBUG_TIMES=1: per-CTA start / drain / end stamps, printed by rtb_sync */

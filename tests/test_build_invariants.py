@@ -34,14 +34,16 @@ def test_register_budgets_of_the_two_kernels(log):
         if counted == "Lb0":                                 # (the counting variant is an untimed instrumentation build)
             assert regs <= 168, f"quad_kernel<{counted}> uses {regs} registers: fewer than 3 CTAs of 128 threads fit an SM"
         assert st <= 128 and ld <= 128, (st, ld)
-        regs, st, ld = _ptxas(log, "persistent_kernelI" + counted)
-        assert regs <= 96, f"persistent_kernel<{counted}> uses {regs} registers: a 640-thread CTA no longer fits"
+        regs, st, ld = _ptxas(log, "persistent_kernelI" + counted + "ELi640E")
+        assert regs <= 96, f"persistent_kernel<{counted}, 640> uses {regs} registers: a 640-thread CTA no longer fits"
         assert st <= 1024 and ld <= 1024, (st, ld)           # spills exist, outside the scan loops (checked in the SASS when they change)
+        regs, st, ld = _ptxas(log, "persistent_kernelI" + counted + "ELi768E")      # the 24-warp variant of scenes without tori
+        assert regs <= 80, f"persistent_kernel<{counted}, 768> uses {regs} registers: a 768-thread CTA no longer fits"
 
 
 @pytest.mark.skipif(shutil.which("cuobjdump") is None or not os.path.isfile(LIB), reason="needs cuobjdump and the built library")
 def test_sass_has_the_tma_bulk_copy_and_the_packed_fp32_instructions():
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN10rtb_strict17persistent_kernelILb0EEEv11FrameParams", LIB],
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN10rtb_strict17persistent_kernelILb0ELi640EEEv11FrameParams", LIB],
                           capture_output=True, text=True, timeout=600).stdout
     assert "sm_100a" in sass
     assert sass.count("UBLKCP") >= 1                         # cp.async.bulk of the packed scene (stage_scene_tma)

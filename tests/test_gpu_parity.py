@@ -460,3 +460,29 @@ def test_cost_ordered_tiles_render_the_same_frames(strict, procedural):
     assert not np.array_equal(frames[1][2], frames[1][3])         # the camera did move
     work = [{k: v for k, v in frames[lpt][4].items() if not k.endswith("_ms")} for lpt in (0, 1)]
     assert work[0] == work[1] and work[0]["dk_iterations"] > 0
+
+
+@pytest.mark.parametrize("case", ("spheres4k/12", "mixed1024/16"))
+def test_the_24_warp_variant_of_the_persistent_kernel_renders_the_same_bits(case, procedural):
+    """Option "wide": scenes without tori run the persistent kernel with 24 warps and 80 registers per thread instead of 20 and 96
+    (automatic; forced on here for a scene with tori as well).  Same code, another register budget: both builds give the bits
+    and the work counters of the 20-warp variant."""
+    sc = CASES[case]()
+    w, h = int(sc.scene["canvas_width"]), int(sc.scene["canvas_height"])
+    for strict in (1, 0):
+        out = {}
+        for wide in (0, 1):
+            gl = rtb200.GLWrapper(w, h)
+            gl.init_window()
+            try:
+                rtb200.setup_scene(gl, sc, procedural)
+                gl.set_option("kernel", KERNEL_PERSISTENT)
+                gl.set_option("strict", strict)
+                gl.set_option("wide", wide)
+                st = gl.draw_counted()
+                assert st.block == (768 if wide else 640)
+                out[wide] = (gl.read_pixels(), {k: v for k, v in st.as_dict().items() if k not in ("kernel_ms", "block", "smem_bytes", "grid")})
+            finally:
+                gl.stop()
+        assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32)), (case, strict)
+        assert out[0][1] == out[1][1], (case, strict)

@@ -10,4 +10,4 @@ cp $ROOT/raytracing-opengl_b200/csrc/*.cu $ROOT/raytracing-opengl_b200/csrc/*.cu
 cp $ROOT/include/*.h $dst/include/
 make -C $dst/pkg/csrc -j4 EXTRA="$*" >/dev/null 2>$dst/make.err || { cat $dst/make.err; exit 1; }
 cp $dst/pkg/librtb200.so $dst/librtb200.so
-grep -A2 "persistent_kernelILb0" $dst/pkg/csrc/ptxas_strict.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $name strict persistent"
+grep -A2 "persistent_kernelILb0ELi640" $dst/pkg/csrc/ptxas_strict.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $name strict persistent"

@@ -6,7 +6,7 @@ import rtb200
 from rtb200 import scenes, textures
 ts = textures.procedural_textures(cube_size=256)
 cube = textures.TextureSet(cube=ts.cube)
-for name, strict, part in (("mixed1024_4k", 0, None), ("mixed1024_4k", 1, None), ("spheres4k", 0, None), ("tori1080", 0, None),
+for name, strict, part in (("mixed1024_4k", 0, None), ("mixed1024_4k", 1, None), ("spheres4k", 0, None), ("spheres4k", 1, None), ("tori1080", 0, None),
                            ("mixed1024_4k", 0, (0, 8)), ("mixed1024_4k", 0, (3, 8)), ("mixed1024_4k", 1, (2, 8)), ("mixed1024_8k", 0, (5, 8))):
     sc = scenes.build_config(name)
     w, h = int(sc.scene["canvas_width"]), int(sc.scene["canvas_height"])

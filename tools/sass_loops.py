@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 obj = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "raytracing-opengl_b200", "csrc", "rt_kernels_strict.o")
-fun = sys.argv[2] if len(sys.argv) > 2 else "_ZN10rtb_strict17persistent_kernelILb0EEEv11FrameParams"
+fun = sys.argv[2] if len(sys.argv) > 2 else "_ZN10rtb_strict17persistent_kernelILb0ELi640EEEv11FrameParams"
 out = subprocess.run(["cuobjdump", "-sass", "-fun", fun, obj], capture_output=True, text=True).stdout
 ins = []
 for line in out.splitlines():
