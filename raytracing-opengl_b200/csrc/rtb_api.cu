@@ -367,7 +367,7 @@ int rtb_do_render(rtb_ctx* ctx, float* target, bool target_global_rows, cudaStre
     }
     /* cost-ordered tiles (option "lpt": -1 = automatic, frames of at least 4096 tiles on the persistent kernel) */
     const int n_tiles = P.n_tiles_x * P.n_tiles_y;
-    const bool lpt = kernel == RTB_KERNEL_PERSISTENT && (ctx->opt_lpt > 0 || (ctx->opt_lpt < 0 && n_tiles >= 4096));
+    const bool lpt = kernel == RTB_KERNEL_PERSISTENT && n_tiles > 0 && (ctx->opt_lpt > 0 || (ctx->opt_lpt < 0 && n_tiles >= 4096));
     if (lpt) {
         if (ctx->lpt_tiles != n_tiles) {                   /* first frame, or the partition changed: no order yet */
             if (ctx->tile_cost) { CU(cudaFreeAsync(ctx->tile_cost, ctx->stream)); CU(cudaFreeAsync(ctx->tile_perm, ctx->stream)); CU(cudaFreeAsync(ctx->tile_hist, ctx->stream)); }
