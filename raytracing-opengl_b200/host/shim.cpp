@@ -20,6 +20,9 @@ struct GLFWwindow {
 namespace {
 long g_frames_presented = 0;
 std::chrono::steady_clock::time_point g_first_present;          /* wall clock of the frame loop (the reference prints FPS, main.cpp:158-174) */
+std::chrono::steady_clock::time_point g_last_present;
+double g_max_gap = 0.0, g_sum_small = 0.0;                      /* the longest frame (a stall of the box shows up here, not in the mean of the others) */
+long g_max_gap_frame = 0, g_n_small = 0;
 GLenum g_active_unit = GL_TEXTURE0;
 GLuint g_bound_2d[8] = { 0 };
 }
@@ -33,9 +36,12 @@ GLFWwindow* rtb_shim_create_window(GLWrapper* owner, int frames) {
 void rtb_shim_destroy_window(GLFWwindow* w) {
     if (g_frames_presented > 1) {
         /* frames 2..N: update_scene + update_buffers (host -> device) + draw + present, as the unchanged loop runs them */
-        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - g_first_present).count();
+        /* up to the LAST present: what follows (stop(), the destructors, cudaFree) is teardown, not the loop — it took up to 0.7 s in some runs */
+        const double s = std::chrono::duration<double>(g_last_present - g_first_present).count();
         printf("frame loop: %ld frames in %.3f s after the first = %.3f ms per frame, %.1f frames/s\n", g_frames_presented - 1, s,
                s * 1e3 / (double)(g_frames_presented - 1), (double)(g_frames_presented - 1) / s);
+        printf("frame loop: longest frame %.3f ms (frame %ld); %.3f ms per frame without the frames longer than 20 ms (%ld of them)\n", g_max_gap * 1e3,
+               g_max_gap_frame, g_n_small ? g_sum_small * 1e3 / (double)g_n_small : 0.0, g_frames_presented - 1 - g_n_small);
     }
     delete w;
 }
@@ -47,7 +53,14 @@ void glfwPollEvents(void) {}
 void glfwSwapInterval(int) {}
 void glfwSwapBuffers(GLFWwindow* w) {
     if (w && w->owner) w->owner->present();
-    if (g_frames_presented == 0) g_first_present = std::chrono::steady_clock::now();
+    const auto now = std::chrono::steady_clock::now();
+    if (g_frames_presented == 0) g_first_present = now;
+    else {
+        const double gap = std::chrono::duration<double>(now - g_last_present).count();
+        if (gap > g_max_gap) { g_max_gap = gap; g_max_gap_frame = g_frames_presented; }
+        if (gap < 0.020) { g_sum_small += gap; g_n_small++; }
+    }
+    g_last_present = now;
     g_frames_presented++;
     if (w && --w->frames_left <= 0) w->should_close = 1;
 }
