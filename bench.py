@@ -488,7 +488,10 @@ def run_ours(args):
                                     "instead of quaternion sandwiches) rather than pipe utilisation"}
         except Exception:
             pass
-        n_launch = args.steps * (world + (1 if world > 1 and args.gather == "cabi" else 0))
+        # kernels of ours per timed step: every rank's ray-trace kernel, its three tile-order kernels (persistent kernel, >= 4096 tiles:
+        # option "lpt"), and the root's de-interleave pass behind the NCCL fan-in
+        lpt_on = kstats.kernel_used == 2 and ((w + 7) // 8) * ((h // world + 3) // 4) >= 4096
+        n_launch = args.steps * (world * (4 if lpt_on else 1) + (1 if world > 1 and args.gather == "cabi" else 0))
         line = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
