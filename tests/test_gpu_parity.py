@@ -424,6 +424,33 @@ def test_cooperative_drain_is_bit_identical_to_the_serial_drain(seed, procedural
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_cost_ordered_tiles_of_one_share_of_a_partition(procedural):
+    """The tile order lives in local tile numbers: rank 3 of an 8-way split (4-scanline blocks) renders the same rows with the
+    option on (second and third frame: ordered) and off, and moving the context to another rank drops the old order."""
+    sc = scenes.build_config("mixed1024_4k", 1 / 3)                # 1280x720
+    w, h = int(sc.scene["canvas_width"]), int(sc.scene["canvas_height"])
+    rows = {}
+    for lpt in (0, 1):
+        gl = rtb200.GLWrapper(w, h)
+        gl.init_window()
+        try:
+            rtb200.setup_scene(gl, sc, procedural)
+            gl.set_option("strict", 0)
+            gl.set_option("lpt", lpt)
+            out = []
+            for rank in (3, 5):
+                gl.set_partition(rank, 8, 4)
+                for _ in range(3):
+                    gl.draw()
+                out.append(gl.read_pixels().copy())
+            rows[lpt] = out
+        finally:
+            gl.stop()
+    for a, b in zip(rows[0], rows[1]):
+        assert a.shape[0] in (88, 92) and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert not np.array_equal(rows[1][0][:88], rows[1][1][:88])
+
+
 @pytest.mark.parametrize("strict", (1, 0))
 def test_cost_ordered_tiles_render_the_same_frames(strict, procedural):
     """Option "lpt": from the second frame on the persistent kernel hands its tiles out costliest first (the order is a
