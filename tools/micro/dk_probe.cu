@@ -92,9 +92,30 @@ DEV void DKstep_p2(f2& c, f2 c1, f2 c2, f2 c3, const TorusP& T, float& E) {
     c = fsub2(c, pk(gx, gy));
     E = max3_nan_abs(E, gx, gy);
 }
+/* VARIANT 17: only cTorus packed — (x, x) * (x, y) = (x^2, x y) as one FMUL2, u = x^2 - y^2 written over the low half, then A and B as two
+ * FFMA2 each on the pairs (u, w) and (x, y); differences, products, inverse and update scalar.  Roots live in (re, im) pairs. */
+DEV void DKstep_p3(f2& c, f2 c1, f2 c2, f2 c3, const TorusP& T, float& E) {
+    const float x = lo(c), y = hi(c);
+    const f2 sq = fmul2(pk(x, x), c);                                  /* (x^2, x y) */
+    const f2 uw = pk(fmaf(-y, y, lo(sq)), hi(sq));
+    const f2 A = ffma2(uw, T.al, ffma2(c, T.be, T.k0));
+    const f2 B = ffma2(uw, T.ga, ffma2(c, T.de, T.rho));
+    const float Ax = lo(A), Ay = hi(A);
+    const float fx = fmaf(Ax, Ax, -fmaf(Ay, Ay, lo(B)));
+    const float fy = fmaf(Ax + Ax, Ay, -hi(B));
+    const float ax = x - lo(c1), ay = y - hi(c1), bx = x - lo(c2), by = y - hi(c2), cx = x - lo(c3), cy = y - hi(c3);
+    const float qx = fmaf(bx, cx, -(by * cy)), qy = fmaf(bx, cy, by * cx);
+    const float px = fmaf(ax, qx, -(ay * qy)), py = fmaf(ax, qy, ay * qx);
+    const float sx = px * 9.5367431640625e-07f, sy = py * 9.5367431640625e-07f;
+    const float r = rcp_mufu(fmaf(sx, px, sy * py));
+    const float ix = sx * r, iy = -sy * r;
+    const float gx = fmaf(fx, ix, -(fy * iy)), gy = fmaf(fx, iy, fy * ix);
+    c = pk(x - gx, y - gy);
+    E = max3_nan_abs(E, gx, gy);
+}
 #if VARIANT == 8
 #define DKstep_f(a, b, c, d, e, f, g, h, T, E) DKstep_a(a, b, c, d, e, f, g, h, T, E, one, nz)
-#elif VARIANT
+#elif VARIANT && VARIANT != 17
 #define DKstep_f DKstep_v
 #endif
 
@@ -110,7 +131,10 @@ __global__ void __launch_bounds__(1024) dk_kernel(const float* __restrict__ in, 
     (void)one; (void)nz;
     __syncthreads();
     const long long t0 = clock64();
-#if VARIANT == 16
+#if VARIANT == 16 || VARIANT == 17
+#if VARIANT == 17
+#define DKstep_p2 DKstep_p3
+#endif
     TorusP TP;
     TP.be = pk(T.be, T.be); TP.k0 = pk(T.k0, 0.f); TP.al = pk(T.al, T.al2); TP.de = pk(T.de, T.de); TP.rho = pk(T.rho, 0.f); TP.ga = pk(T.ga, T.ga2);
     f2 c0 = pk(x0, y0), c1 = pk(x1, y1), c2 = pk(x2, y2), c3 = pk(x3, y3);
