@@ -179,8 +179,8 @@ double algorithmic_flops(const rtb_stats& s) {
  * the CTA with the longest leftovers ends the frame (measured: 3 200 drain jobs against a median of 1 900).  So the cheapest
  * tiles of the previous frame (cost = summed path lengths of the tile's 32 pixels; as many as `tail`, taken bucket by bucket
  * from the cheap end) go LAST, costliest bucket first, and all other tiles keep the scan order.  Measured (tools/lpt_ab.py,
- * profiles/r2_lpt_ab.jsonl): whole 4K frames 0.3-1.7 % faster, one share of an 8-way split 2.4-3.2 % (the drain is 10 % of
- * such a frame).  Sorting the WHOLE frame by cost gains 3.9 % on a share but loses 1-2.4 % on whole frames: neighbouring
+ * profiles/r2_lpt_ab.jsonl): whole 4K frames 0.3-1.9 % faster, one share of an 8-way split 3.5-4.2 % (the drain is 10 % of
+ * such a frame).  Sorting the WHOLE frame by cost gains the same on a share but loses 1-2.4 % on whole frames: neighbouring
  * lanes then hold unrelated pixels.  Three small kernels (histogram per 4096-tile chunk, plan, scatter). */
 __device__ __forceinline__ unsigned cost_bucket(unsigned c) { c >>= 2; return c > 255u ? 255u : c; }
 constexpr int ORDER_CHUNK = 4096;                                  /* tiles per CTA: four consecutive ones per thread */
