@@ -189,6 +189,11 @@ void* rtb_device_framebuffer(rtb_ctx* ctx);
 
 int rtb_get_stats(rtb_ctx* ctx, rtb_stats* out);
 
+/* Inspection of the cost-ordered tile hand-out (option "lpt"): the per-tile costs of the last frame (summed path lengths of the
+ * tile's 32 pixels) and the hand-out order derived from them for the next frame, `capacity` entries each at most; returns the
+ * number of tiles (0: the option is off or no frame has been rendered), negative on error.  Either pointer may be NULL. */
+int rtb_tile_order(rtb_ctx* ctx, uint32_t* cost, uint32_t* order, int capacity);
+
 /* FFMA-only microbenchmark: measured fp32 CUDA-core peak of `device` in
  * TFLOP/s (the roofline denominator; MEASURED_PEAKS.json has none). */
 int rtb_measure_fp32_peak(int device, double* tflops);

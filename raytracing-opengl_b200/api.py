@@ -92,6 +92,7 @@ def load_library() -> C.CDLL:
     L.rtb_device_framebuffer.restype = vp
     L.rtb_device_framebuffer.argtypes = [vp]
     L.rtb_get_stats.argtypes = [vp, C.POINTER(RtbStats)]
+    L.rtb_tile_order.argtypes = [vp, vp, vp, i]
     L.rtb_measure_fp32_peak.argtypes = [i, C.POINTER(C.c_double)]
     L.rtb_measure_fp32_peak3.argtypes = [i, C.POINTER(C.c_double)]
     L.rtb_last_error.restype = C.c_char_p
@@ -281,6 +282,17 @@ class GLWrapper:
     def draw_to(self, device_ptr: int, stream: int = 0):
         """Render into a caller-owned device buffer (e.g. a torch tensor's data_ptr) on a caller stream."""
         self._check(self._L.rtb_render_to(self._ctx, device_ptr, stream or None))
+
+    def tile_order(self):
+        """(cost, order) of the cost-ordered tile hand-out (option "lpt") after the last frame, or None while there is none."""
+        n = self._L.rtb_tile_order(self._ctx, None, None, 0)
+        if n < 0:
+            self._check(n)
+        if n == 0:
+            return None
+        cost, order = np.empty(n, np.uint32), np.empty(n, np.uint32)
+        self._check(min(0, self._L.rtb_tile_order(self._ctx, cost.ctypes.data, order.ctypes.data, n)))
+        return cost, order
 
     def draw_counted(self) -> RtbStats:
         st = RtbStats()

@@ -724,6 +724,17 @@ int rtb_read_rgba8(rtb_ctx* ctx, uint8_t* dst) {
     return RTB_OK;
 }
 
+int rtb_tile_order(rtb_ctx* ctx, uint32_t* cost, uint32_t* order, int capacity) {
+    if (!ctx || capacity < 0) { fail(ctx, RTB_ERR_INVALID, "bad argument"); return RTB_ERR_INVALID; }
+    if (!ctx->lpt_valid || !ctx->tile_cost) return 0;
+    int rc = rtb_sync(ctx);
+    if (rc) return rc;
+    const int n = ctx->lpt_tiles < capacity ? ctx->lpt_tiles : capacity;
+    if (cost && cudaMemcpy(cost, ctx->tile_cost, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) { fail(ctx, RTB_ERR_CUDA, "cudaMemcpy"); return RTB_ERR_CUDA; }
+    if (order && cudaMemcpy(order, ctx->tile_perm, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) { fail(ctx, RTB_ERR_CUDA, "cudaMemcpy"); return RTB_ERR_CUDA; }
+    return ctx->lpt_tiles;
+}
+
 void* rtb_device_framebuffer(rtb_ctx* ctx) { return ctx ? (ctx->fb_full ? ctx->fb_full : ctx->fb) : nullptr; }
 
 }  // extern "C"

@@ -513,3 +513,32 @@ def test_the_24_warp_variant_of_the_persistent_kernel_renders_the_same_bits(case
                 gl.stop()
         assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32)), (case, strict)
         assert out[0][1] == out[1][1], (case, strict)
+
+
+def test_the_tile_order_is_a_permutation_with_the_cheapest_tiles_last(procedural):
+    """rtb_tile_order: after a frame the hand-out order of the next one is a permutation of the tiles whose tail holds the
+    cheapest tiles (3 x the tiles in flight, at most half the frame; by cost bucket, costliest first) and whose head keeps
+    the scan order."""
+    sc = scenes.build_config("mixed1024_4k", 1 / 3)                # 1280x720: 14 400 tiles, the option is on by itself
+    w, h = int(sc.scene["canvas_width"]), int(sc.scene["canvas_height"])
+    gl = rtb200.GLWrapper(w, h)
+    gl.init_window()
+    try:
+        rtb200.setup_scene(gl, sc, procedural)
+        gl.set_option("strict", 0)
+        assert gl.tile_order() is None
+        gl.draw()
+        cost, order = gl.tile_order()
+        st = gl.stats()
+    finally:
+        gl.stop()
+    n = ((w + 7) // 8) * ((h + 3) // 4)
+    assert len(order) == n and np.array_equal(np.sort(order), np.arange(n, dtype=np.uint32))
+    assert cost.min() >= 32 and int(cost.sum()) >= 32 * n         # every pixel's path has at least length 1
+    tail = min(3 * (st.grid * st.block // 32), n // 2)
+    head_t, tail_t = order[: n - tail], order[n - tail:]
+    bucket = np.minimum(cost >> 2, 255)
+    assert np.all(np.diff(head_t.astype(np.int64)) > 0)             # scan order
+    assert bucket[tail_t].max() <= bucket[head_t].min()
+    assert np.all(np.diff(bucket[tail_t].astype(np.int64)) <= 0)    # costliest bucket of the tail first
+    assert bucket[tail_t][-1] == bucket.min()
