@@ -540,10 +540,10 @@ def run_ours(args):
 
 def main():
     # stdout carries the ONE JSON line and nothing else: this image exports NCCL_DEBUG=VERSION, which makes NCCL print its banner
-    # ("NCCL version ...") to stdout at the first communicator; any other NCCL_DEBUG setting is left alone, with its log on stderr
+    # ("NCCL version ...") to stdout at the first communicator.  Any other NCCL_DEBUG setting (INFO, ...) is left exactly as the
+    # caller made it, log destination included.
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "NONE"
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse()
     if args.impl == "reference":
         run_reference(args)
