@@ -539,11 +539,8 @@ def run_ours(args):
 
 
 def main():
-    # stdout carries the ONE JSON line and nothing else: this image exports NCCL_DEBUG=VERSION, which makes NCCL print its banner
-    # ("NCCL version ...") to stdout at the first communicator.  Any other NCCL_DEBUG setting (INFO, ...) is left exactly as the
-    # caller made it, log destination included.
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "NONE"
+    # (At N > 1 this image's NCCL_DEBUG=VERSION makes NCCL itself print a "NCCL version ..." banner to stdout before the JSON line; it is
+    # left alone on purpose — NCCL's log level and destination belong to whoever launches the benchmark.)
     args = parse()
     if args.impl == "reference":
         run_reference(args)
